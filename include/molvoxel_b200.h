@@ -1,0 +1,124 @@
+/*
+ * molvoxel_b200.h — C ABI of the B200-native voxelization backend (libmolvoxel_b200.so).
+ *
+ * Drop-in boundary: this is what a `library="b200"` branch of the reference factory
+ * (reference molvoxel/__init__.py:25-40) binds.  One call voxelizes a CSR batch of molecules
+ * — the batched form of reference numpy/voxelizer.py forward_types (:240-315),
+ * forward_features (:97-169) and forward_single (:370-436); B = 1 is the reference's
+ * per-molecule call.  Plain pointers and sizes only: no torch / C++ types cross this boundary.
+ *
+ * All functions return MVX_OK (0) or a negative mvx_status; none throws.  mvx_last_error()
+ * returns a thread-local message for the last failure on the calling thread.
+ */
+#ifndef MOLVOXEL_B200_H
+#define MOLVOXEL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVX_VERSION 100 /* 0.1.0 */
+
+typedef enum mvx_status {
+    MVX_OK = 0,
+    MVX_ERR_NULL_POINTER = -1,
+    MVX_ERR_BAD_ENUM = -2,
+    MVX_ERR_BAD_SHAPE = -3,      /* the reference's shape asserts, numpy/voxelizer.py:171-192,317-342,438-455 */
+    MVX_ERR_WORKSPACE = -4,      /* workspace too small / misaligned */
+    MVX_ERR_CUDA = -5,           /* a CUDA runtime call failed */
+    MVX_ERR_UNSUPPORTED = -6,    /* e.g. forward_single with channel-wise radii (numpy/voxelizer.py:443) */
+    MVX_ERR_DEVICE_FLAG = -7     /* device-side validation failed (type out of range, radius > max_radius) */
+} mvx_status;
+
+enum { MVX_DENSITY_GAUSSIAN = 0, MVX_DENSITY_BINARY = 1 };          /* base/voxelizer.py:13 */
+enum { MVX_RADII_SCALAR = 0, MVX_RADII_CHANNEL_WISE = 1, MVX_RADII_ATOM_WISE = 2 }; /* base/voxelizer.py:12 */
+enum { MVX_MODE_SINGLE = 0, MVX_MODE_TYPES = 1, MVX_MODE_FEATURES = 2 };            /* base/voxelizer.py:121-128 */
+enum { MVX_F32 = 0, MVX_F64 = 1 };
+
+/* Constructor arguments of the reference Voxelizer (base/voxelizer.py:15-38, numpy/voxelizer.py:22-35). */
+typedef struct mvx_grid_spec {
+    double  resolution;       /* Angstrom per voxel */
+    int32_t dimension;        /* D = H = W, 1..512 */
+    int32_t density_type;     /* MVX_DENSITY_* */
+    double  sigma;            /* Gaussian sigma (kwarg `sigma`, default 0.5) */
+    int32_t radii_type;       /* MVX_RADII_* */
+    int32_t compat_blockdim;  /* the reference `blockdim` whose half-voxel block cull is emulated
+                                 (numpy/voxelizer.py:55,496-527; default 8).  <= 0 or >= dimension:
+                                 exact mathematics (the reference with blockdim = dimension). */
+} mvx_grid_spec;
+
+/*
+ * One batch of molecules in CSR form.  Every pointer is a DEVICE pointer for mvx_voxelize and a
+ * HOST pointer for mvx_voxelize_host.  Argument meaning follows the reference forward_* calls:
+ *   coords   (N,3)  f32|f64  atom coordinates                  (numpy/voxelizer.py:251)
+ *   centers  (B,3)  f32|f64  or NULL = no centring             (:263)
+ *   types    (N,)   int32    channel index per atom, TYPES     (:253)
+ *   features (N,C)  f32      feature rows, FEATURES            (:110)
+ *   radius   python-float scalar when radii_type is SCALAR
+ *   radii    (C,) f32 channel-wise | (N,) f32 atom-wise        (:111)
+ */
+typedef struct mvx_batch {
+    int32_t        mode;            /* MVX_MODE_* */
+    int32_t        num_mols;        /* B */
+    int64_t        total_atoms;     /* N = mol_offsets[B] */
+    const int32_t *mol_offsets;     /* (B+1,) */
+    const void    *coords;
+    int32_t        coords_dtype;    /* MVX_F32 | MVX_F64 */
+    const void    *centers;
+    int32_t        centers_dtype;
+    const int32_t *types;
+    const float   *features;
+    int32_t        num_channels;    /* C: channels the inputs address (types < C; features row length) */
+    int32_t        out_channels;    /* channels of `out` (>= C; surplus channels are zero, :337) */
+    double         radius;
+    const float   *radii;
+    double         max_radius;      /* host-known upper bound of every radius in `radii` (array
+                                       radii types).  For FEATURES + channel-wise it must be the
+                                       exact max: the reference clips with radii.max() (:138). */
+} mvx_batch;
+
+/* Bytes of device workspace mvx_voxelize needs for this spec/batch (256-byte aligned base). */
+int mvx_workspace_bytes(const mvx_grid_spec *spec, const mvx_batch *batch, size_t *out_bytes);
+
+/*
+ * Voxelize a batch: out is a DEVICE buffer (B, out_channels, D, H, W) float32, contiguous,
+ * written exactly once per voxel (zeros included).  Work is enqueued on `stream`
+ * (a cudaStream_t; NULL = legacy default stream); no host synchronisation happens inside.
+ */
+int mvx_voxelize(const mvx_grid_spec *spec, const mvx_batch *batch, float *out, void *workspace,
+                 size_t workspace_bytes, void *stream);
+
+/*
+ * Same, with HOST input buffers (what a numpy caller of the reference holds): copies the inputs
+ * to the device, voxelizes into the DEVICE buffer `out`, and copies the device status word back
+ * (one synchronisation).  `workspace` must hold mvx_workspace_bytes() + mvx_host_staging_bytes().
+ * Pinned host memory makes the copies asynchronous but is not required.
+ */
+int mvx_host_staging_bytes(const mvx_grid_spec *spec, const mvx_batch *batch, size_t *out_bytes);
+int mvx_voxelize_host(const mvx_grid_spec *spec, const mvx_batch *host_batch, float *out, void *workspace,
+                      size_t workspace_bytes, void *stream);
+
+/* Reads and clears the device status word of the last mvx_voxelize on this workspace (synchronises `stream`). */
+int mvx_check_status(void *workspace, void *stream);
+
+/* Number of kernels one mvx_voxelize call launches for this spec/batch (bench.py's gpu_launches). */
+int mvx_launches_per_call(const mvx_grid_spec *spec, const mvx_batch *batch);
+
+/*
+ * Per-kernel device timing for bench.py's roofline: between begin and end every mvx_voxelize call on
+ * this thread records CUDA events around its launches on the caller's stream (no synchronisation until
+ * end).  end returns the summed milliseconds of the prep, bin and voxelize launches over the recorded calls.
+ */
+int mvx_profile_begin(int max_calls);
+int mvx_profile_end(double *ms_prep, double *ms_bin, double *ms_voxelize, int *num_calls);
+
+const char *mvx_last_error(void);
+int mvx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOLVOXEL_B200_H */

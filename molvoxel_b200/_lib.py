@@ -1,0 +1,132 @@
+"""Build + ctypes binding of libmolvoxel_b200.so (C ABI: include/molvoxel_b200.h).
+
+The shared library is compiled in-tree by nvcc for sm_100a only.  There is no CPU fallback: if the
+library is missing it is built; if it cannot be built or loaded, importing the binding raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(CSRC, "libmolvoxel_b200.so")
+SOURCES = [os.path.join(CSRC, "mvx_api.cu")]
+HEADERS = [os.path.join(CSRC, "mvx_kernels.cuh"), os.path.join(os.path.dirname(_HERE), "include", "molvoxel_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+MVX_OK = 0
+MVX_ERR_NULL_POINTER, MVX_ERR_BAD_ENUM, MVX_ERR_BAD_SHAPE = -1, -2, -3
+MVX_ERR_WORKSPACE, MVX_ERR_CUDA, MVX_ERR_UNSUPPORTED, MVX_ERR_DEVICE_FLAG = -4, -5, -6, -7
+MVX_F32, MVX_F64 = 0, 1
+DENSITY = {"gaussian": 0, "binary": 1}
+RADII = {"scalar": 0, "channel-wise": 1, "atom-wise": 2}
+MODE = {"single": 0, "types": 1, "features": 2}
+
+
+class GridSpec(ctypes.Structure):
+    _fields_ = [
+        ("resolution", ctypes.c_double),
+        ("dimension", ctypes.c_int32),
+        ("density_type", ctypes.c_int32),
+        ("sigma", ctypes.c_double),
+        ("radii_type", ctypes.c_int32),
+        ("compat_blockdim", ctypes.c_int32),
+    ]
+
+
+class Batch(ctypes.Structure):
+    _fields_ = [
+        ("mode", ctypes.c_int32),
+        ("num_mols", ctypes.c_int32),
+        ("total_atoms", ctypes.c_int64),
+        ("mol_offsets", ctypes.c_void_p),
+        ("coords", ctypes.c_void_p),
+        ("coords_dtype", ctypes.c_int32),
+        ("centers", ctypes.c_void_p),
+        ("centers_dtype", ctypes.c_int32),
+        ("types", ctypes.c_void_p),
+        ("features", ctypes.c_void_p),
+        ("num_channels", ctypes.c_int32),
+        ("out_channels", ctypes.c_int32),
+        ("radius", ctypes.c_double),
+        ("radii", ctypes.c_void_p),
+        ("max_radius", ctypes.c_double),
+    ]
+
+
+def _stale() -> bool:
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    return any(os.path.exists(p) and os.path.getmtime(p) > t for p in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library for sm_100a (nvcc cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return SO_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("molvoxel_b200: nvcc not found and libmolvoxel_b200.so is missing/stale")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + SOURCES
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("molvoxel_b200: nvcc failed:\n" + proc.stdout + proc.stderr)
+    if verbose:
+        print(proc.stderr)
+    return SO_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library (built on first use when nvcc is present)."""
+    global _lib
+    if _lib is None:
+        if _stale():
+            build()
+        L = ctypes.CDLL(SO_PATH)
+        vp, sz = ctypes.c_void_p, ctypes.c_size_t
+        L.mvx_version.restype = ctypes.c_int
+        L.mvx_last_error.restype = ctypes.c_char_p
+        L.mvx_workspace_bytes.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch), ctypes.POINTER(sz)]
+        L.mvx_host_staging_bytes.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch), ctypes.POINTER(sz)]
+        L.mvx_voxelize.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch), vp, vp, sz, vp]
+        L.mvx_voxelize_host.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch), vp, vp, sz, vp]
+        L.mvx_check_status.argtypes = [vp, vp]
+        L.mvx_launches_per_call.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch)]
+        L.mvx_profile_begin.argtypes = [ctypes.c_int]
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.mvx_profile_end.argtypes = [dp, dp, dp, ctypes.POINTER(ctypes.c_int)]
+        L.mvx_profile_begin.restype = L.mvx_profile_end.restype = ctypes.c_int
+        for fn in (L.mvx_workspace_bytes, L.mvx_host_staging_bytes, L.mvx_voxelize, L.mvx_voxelize_host,
+                   L.mvx_check_status, L.mvx_launches_per_call):
+            fn.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+EXPORTED_SYMBOLS = [
+    "mvx_version", "mvx_last_error", "mvx_workspace_bytes", "mvx_host_staging_bytes", "mvx_voxelize",
+    "mvx_voxelize_host", "mvx_check_status", "mvx_launches_per_call", "mvx_profile_begin", "mvx_profile_end",
+]
+
+
+def raise_for_status(rc: int):
+    """Map a C-ABI status to the reference's exception conventions."""
+    if rc == MVX_OK:
+        return
+    msg = lib().mvx_last_error().decode("utf-8", "replace")
+    if rc in (MVX_ERR_BAD_SHAPE, MVX_ERR_UNSUPPORTED):
+        raise AssertionError(msg)          # the reference raises AssertionError from bare asserts
+    if rc in (MVX_ERR_BAD_ENUM, MVX_ERR_DEVICE_FLAG, MVX_ERR_NULL_POINTER):
+        raise ValueError(msg)
+    raise RuntimeError(f"molvoxel_b200 (status {rc}): {msg}")

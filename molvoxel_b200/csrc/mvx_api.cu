@@ -1,0 +1,415 @@
+// mvx_api.cu — C ABI of libmolvoxel_b200.so (declared in include/molvoxel_b200.h).
+// Host-side plumbing only: argument checks mirroring the reference's asserts, workspace carving,
+// kernel dispatch.  No torch, no CPU compute fallback: without a CUDA device every entry point
+// that would launch work fails with MVX_ERR_CUDA.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/molvoxel_b200.h"
+#include "mvx_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define MVX_CUDA_OK(expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(MVX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));        \
+    } while (0)
+
+constexpr size_t kAlign = 256;
+
+// Optional per-kernel timing (bench.py's roofline): CUDA events recorded around each launch on the
+// caller's stream while a profile is open.  No synchronisation until mvx_profile_end.
+struct Profile {
+    bool active = false;
+    int max_calls = 0, calls = 0;
+    cudaEvent_t* ev = nullptr;   // 4 events per call: before prep, after prep, after bin, after voxelize
+};
+thread_local Profile g_prof;
+
+void prof_mark(cudaStream_t st, int slot) {
+    if (g_prof.active && g_prof.calls < g_prof.max_calls) cudaEventRecord(g_prof.ev[g_prof.calls * 4 + slot], st);
+}
+size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+struct Plan {
+    mvx::Geo geo;
+    int ncol, nzc, tz, maxcols, nv;
+    float tau_lin, tau_quad;
+    // workspace offsets (bytes)
+    size_t off_status, off_recs, off_colrange, off_bins, off_lists, total;
+};
+
+int check_args(const mvx_grid_spec* s, const mvx_batch* b) {
+    if (!s || !b) return fail(MVX_ERR_NULL_POINTER, "spec/batch is NULL");
+    if (s->dimension < 1 || s->dimension > 512) return fail(MVX_ERR_BAD_SHAPE, "dimension must be in 1..512");
+    if (!(s->resolution > 0.0)) return fail(MVX_ERR_BAD_SHAPE, "resolution must be positive");
+    if (s->density_type != MVX_DENSITY_GAUSSIAN && s->density_type != MVX_DENSITY_BINARY)
+        return fail(MVX_ERR_BAD_ENUM, "density_type");
+    if (s->radii_type < MVX_RADII_SCALAR || s->radii_type > MVX_RADII_ATOM_WISE) return fail(MVX_ERR_BAD_ENUM, "radii_type");
+    if (b->mode < MVX_MODE_SINGLE || b->mode > MVX_MODE_FEATURES) return fail(MVX_ERR_BAD_ENUM, "mode");
+    if (s->density_type == MVX_DENSITY_GAUSSIAN && !(s->sigma > 0.0)) return fail(MVX_ERR_BAD_SHAPE, "sigma must be positive");
+    if (b->num_mols < 0 || b->total_atoms < 0) return fail(MVX_ERR_BAD_SHAPE, "negative batch size");
+    if (b->total_atoms > 0x7fffffffLL) return fail(MVX_ERR_BAD_SHAPE, "more than 2^31-1 atoms in one batch");
+    if (b->mode == MVX_MODE_SINGLE && s->radii_type == MVX_RADII_CHANNEL_WISE)
+        return fail(MVX_ERR_UNSUPPORTED, "Channel-Wise Radii Type is not supported");   // numpy/voxelizer.py:443
+    const int C = b->mode == MVX_MODE_SINGLE ? 1 : b->num_channels;
+    if (C < 1) return fail(MVX_ERR_BAD_SHAPE, "num_channels must be >= 1");
+    if (b->out_channels < C)   // numpy/voxelizer.py:337 (types), :192 (features), :450 (single)
+        return fail(MVX_ERR_BAD_SHAPE, "Output channel is less than number of types");
+    if (b->mode != MVX_MODE_TYPES && b->out_channels != C) return fail(MVX_ERR_BAD_SHAPE, "Output grid dimension incorrect");
+    if (b->num_mols > 0 && !b->mol_offsets) return fail(MVX_ERR_NULL_POINTER, "mol_offsets");
+    if (b->total_atoms > 0) {
+        if (!b->coords) return fail(MVX_ERR_NULL_POINTER, "coords");
+        if (b->mode == MVX_MODE_TYPES && !b->types) return fail(MVX_ERR_NULL_POINTER, "types");
+        if (b->mode == MVX_MODE_FEATURES && !b->features) return fail(MVX_ERR_NULL_POINTER, "features");
+    }
+    if (s->radii_type == MVX_RADII_SCALAR) {
+        if (!(b->radius > 0.0)) return fail(MVX_ERR_BAD_SHAPE, "the radii type of voxelizer is `scalar`, radii should be a positive scalar");
+    } else {
+        if (!b->radii && (b->total_atoms > 0 || s->radii_type == MVX_RADII_CHANNEL_WISE))
+            return fail(MVX_ERR_NULL_POINTER, "radii");
+        if (!(b->max_radius > 0.0)) return fail(MVX_ERR_BAD_SHAPE, "max_radius must bound the radii array");
+    }
+    return MVX_OK;
+}
+
+int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
+    int rc = check_args(s, b);
+    if (rc != MVX_OK) return rc;
+    mvx::Geo& g = pl->geo;
+    const int D = s->dimension;
+    g.res = s->resolution;
+    const double width = s->resolution * (double)(D - 1);   // base/voxelizer.py:28
+    g.half_width = width / 2.0;                            // numpy/voxelizer.py:42
+    g.res_half = s->resolution / 2.0;                      // :55
+    g.upper = width / 2.0;                                 // base/voxelizer.py:33
+    g.lower = -1 * g.upper;                                // base/voxelizer.py:34
+    g.sigma = s->sigma;
+    g.dim = D;
+    g.bd = (s->compat_blockdim <= 0 || s->compat_blockdim >= D) ? D : s->compat_blockdim;
+    g.nb = (D + g.bd - 1) / g.bd;
+    g.ncx = (D + mvx::kTile - 1) / mvx::kTile;
+
+    const bool chan_feat = b->mode == MVX_MODE_FEATURES && s->radii_type == MVX_RADII_CHANNEL_WISE;
+    g.scalar_form = (s->radii_type == MVX_RADII_SCALAR) || chan_feat;
+    double reach;
+    if (s->radii_type == MVX_RADII_SCALAR) {
+        g.radii_src = 0;
+        g.size_scalar = b->radius;
+        g.r_scalar32 = (float)b->radius;
+        g.clip_lo = g.lower - b->radius;     // numpy/voxelizer.py:487
+        g.clip_hi = g.upper + b->radius;     // :488
+        reach = std::fmax(b->radius, (double)g.r_scalar32);
+    } else if (chan_feat) {
+        // atom_size = radii.max() is an np.float32 scalar: the python-float bounds are demoted (NEP 50),
+        // so the clip thresholds are fp32 results (numpy/voxelizer.py:138, :487-488)
+        g.radii_src = 3;
+        const float rmax = (float)b->max_radius;
+        g.size_scalar = (double)rmax;
+        g.r_scalar32 = rmax;
+        g.clip_lo = (double)((float)g.lower - rmax);
+        g.clip_hi = (double)((float)g.upper + rmax);
+        reach = (double)rmax;
+    } else {
+        g.radii_src = (s->radii_type == MVX_RADII_ATOM_WISE) ? 1 : 2;
+        g.size_scalar = 0.0;
+        g.r_scalar32 = 0.f;
+        g.clip_lo = g.clip_hi = 0.0;
+        reach = b->max_radius;
+    }
+    const int span = (int)std::ceil(2.0 * reach * (1.0 + 1e-6) / s->resolution + 0.02) + 2;
+    g.cols_axis_max = span / mvx::kTile + 2;
+    if (g.cols_axis_max > g.ncx) g.cols_axis_max = g.ncx;
+    pl->maxcols = g.cols_axis_max * g.cols_axis_max;
+    pl->ncol = g.ncx * g.ncx;
+    pl->nv = (D % 4 == 0) ? 4 : 1;
+    pl->nzc = (D + 63) / 64;
+    int tz = (D + pl->nzc - 1) / pl->nzc;
+    tz = (tz + 3) / 4 * 4;
+    pl->tz = tz;
+    pl->nzc = (D + tz - 1) / tz;
+    // tolerance band of the fp32 cutoff test (see DESIGN.md "cutoff decisions")
+    const double ext = (double)(tz > mvx::kTile ? tz : mvx::kTile) * s->resolution + reach;
+    pl->tau_lin = (float)(21.0 * std::ldexp(1.0, -24) * ext);
+    pl->tau_quad = (float)(12.0 * std::ldexp(1.0, -24));
+
+    const size_t N = (size_t)b->total_atoms, B = (size_t)b->num_mols;
+    size_t off = 0;
+    pl->off_status = off;   off += kAlign;
+    pl->off_recs = off;     off += align_up(N * sizeof(mvx::AtomRec));
+    pl->off_colrange = off; off += align_up(N * sizeof(uint32_t));
+    pl->off_bins = off;     off += align_up(B * (size_t)pl->ncol * sizeof(uint2));
+    pl->off_lists = off;    off += align_up(N * (size_t)pl->maxcols * sizeof(uint32_t));
+    pl->total = off;
+    return MVX_OK;
+}
+
+template <int MODE, int CH, bool BINARY>
+cudaError_t launch_vox_nv(const mvx::VoxParams& vp, int nv, unsigned grid, cudaStream_t st) {
+    if (nv == 4) mvx::mvx_voxelize_kernel<MODE, CH, BINARY, 4><<<grid, mvx::kThreads, 0, st>>>(vp);
+    else mvx::mvx_voxelize_kernel<MODE, CH, BINARY, 1><<<grid, mvx::kThreads, 0, st>>>(vp);
+    return cudaGetLastError();
+}
+
+template <int MODE, int CH>
+cudaError_t launch_vox_density(const mvx::VoxParams& vp, bool binary, int nv, unsigned grid, cudaStream_t st) {
+    return binary ? launch_vox_nv<MODE, CH, true>(vp, nv, grid, st) : launch_vox_nv<MODE, CH, false>(vp, nv, grid, st);
+}
+
+int pick_chunk(int mode, int nchan) {
+    if (mode == MVX_MODE_SINGLE) return 1;
+    if (nchan <= 1) return 1;
+    if (nchan <= 4) return 4;
+    if (nchan <= 8) return 8;
+    return 16;
+}
+
+cudaError_t launch_vox(int mode, int ch, const mvx::VoxParams& vp, bool binary, int nv, unsigned grid, cudaStream_t st) {
+    if (mode == MVX_MODE_SINGLE) return launch_vox_density<0, 1>(vp, binary, nv, grid, st);
+    if (mode == MVX_MODE_TYPES) {
+        switch (ch) {
+            case 1: return launch_vox_density<1, 1>(vp, binary, nv, grid, st);
+            case 4: return launch_vox_density<1, 4>(vp, binary, nv, grid, st);
+            case 8: return launch_vox_density<1, 8>(vp, binary, nv, grid, st);
+            default: return launch_vox_density<1, 16>(vp, binary, nv, grid, st);
+        }
+    }
+    switch (ch) {
+        case 1: return launch_vox_density<2, 1>(vp, binary, nv, grid, st);
+        case 4: return launch_vox_density<2, 4>(vp, binary, nv, grid, st);
+        case 8: return launch_vox_density<2, 8>(vp, binary, nv, grid, st);
+        default: return launch_vox_density<2, 16>(vp, binary, nv, grid, st);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mvx_version(void) { return MVX_VERSION; }
+
+const char* mvx_last_error(void) { return g_last_error.c_str(); }
+
+int mvx_workspace_bytes(const mvx_grid_spec* spec, const mvx_batch* batch, size_t* out_bytes) {
+    if (!out_bytes) return fail(MVX_ERR_NULL_POINTER, "out_bytes is NULL");
+    Plan pl;
+    int rc = make_plan(spec, batch, &pl);
+    if (rc != MVX_OK) return rc;
+    *out_bytes = pl.total;
+    return MVX_OK;
+}
+
+int mvx_launches_per_call(const mvx_grid_spec* spec, const mvx_batch* batch) {
+    Plan pl;
+    int rc = make_plan(spec, batch, &pl);
+    if (rc != MVX_OK) return rc;
+    if (batch->num_mols == 0) return 0;
+    const bool chan_feat = batch->mode == MVX_MODE_FEATURES && spec->radii_type == MVX_RADII_CHANNEL_WISE;
+    int nvox = chan_feat ? batch->num_channels : 1;
+    return (batch->total_atoms > 0 ? 1 : 0) + 1 + nvox;   // prep + bin + voxelize
+}
+
+int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+    Plan pl;
+    int rc = make_plan(spec, batch, &pl);
+    if (rc != MVX_OK) return rc;
+    if (batch->num_mols == 0) return MVX_OK;
+    if (!out) return fail(MVX_ERR_NULL_POINTER, "out is NULL");
+    if (!workspace || workspace_bytes < pl.total) return fail(MVX_ERR_WORKSPACE, "workspace too small");
+    if ((uintptr_t)workspace % kAlign != 0) return fail(MVX_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    if ((uintptr_t)out % 16 != 0) return fail(MVX_ERR_BAD_SHAPE, "out must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    int* status = (int*)(ws + pl.off_status);
+    mvx::AtomRec* recs = (mvx::AtomRec*)(ws + pl.off_recs);
+    uint32_t* colrange = (uint32_t*)(ws + pl.off_colrange);
+    uint2* bins = (uint2*)(ws + pl.off_bins);
+    uint32_t* lists = (uint32_t*)(ws + pl.off_lists);
+
+    const int B = batch->num_mols;
+    const int64_t N = batch->total_atoms;
+    const int C = batch->mode == MVX_MODE_SINGLE ? 1 : batch->num_channels;
+    MVX_CUDA_OK(cudaMemsetAsync(status, 0, kAlign, st));
+    prof_mark(st, 0);
+
+    if (N > 0) {
+        mvx::PrepParams pp;
+        pp.g = pl.geo;
+        pp.mode = batch->mode; pp.B = B; pp.C = C; pp.N = N;
+        pp.mol_offsets = batch->mol_offsets;
+        pp.coords = batch->coords; pp.coords_f64 = batch->coords_dtype == MVX_F64;
+        pp.centers = batch->centers; pp.centers_f64 = batch->centers_dtype == MVX_F64;
+        pp.types = batch->types; pp.radii = batch->radii;
+        pp.recs = recs; pp.colrange = colrange; pp.status = status;
+        const unsigned grid = (unsigned)((N + 255) / 256);
+        mvx::mvx_prep_kernel<<<grid, 256, 0, st>>>(pp);
+        MVX_CUDA_OK(cudaGetLastError());
+    }
+    prof_mark(st, 1);
+    {
+        mvx::BinParams bp;
+        bp.B = B; bp.ncol = pl.ncol; bp.ncx = pl.geo.ncx; bp.maxcols = pl.maxcols;
+        bp.mol_offsets = batch->mol_offsets; bp.colrange = colrange; bp.bins = bins; bp.lists = lists;
+        const int threads = (N / (B > 0 ? B : 1) > 512) ? 1024 : 256;
+        const size_t smem = 2 * (size_t)pl.ncol * sizeof(uint32_t);
+        mvx::mvx_bin_kernel<<<(unsigned)B, threads, smem, st>>>(bp);
+        MVX_CUDA_OK(cudaGetLastError());
+    }
+    prof_mark(st, 2);
+    {
+        mvx::VoxParams vp;
+        vp.res = pl.geo.res; vp.half_width = pl.geo.half_width; vp.sigma = spec->sigma;
+        vp.tau_lin = pl.tau_lin; vp.tau_quad = pl.tau_quad;
+        vp.dim = spec->dimension; vp.ncx = pl.geo.ncx; vp.ncol = pl.ncol; vp.nzc = pl.nzc; vp.tz = pl.tz;
+        vp.C = C; vp.Cout = batch->out_channels; vp.maxcols = pl.maxcols;
+        vp.mol_offsets = batch->mol_offsets; vp.recs = recs; vp.bins = bins; vp.lists = lists;
+        vp.types = batch->types; vp.features = batch->features; vp.chan_radii = nullptr; vp.out = out;
+        const unsigned long long nblk = (unsigned long long)B * pl.ncol * pl.nzc;
+        if (nblk > 0x7fffffffULL) return fail(MVX_ERR_BAD_SHAPE, "batch too large for one launch; split it");
+        const bool binary = spec->density_type == MVX_DENSITY_BINARY;
+        const bool chan_feat = batch->mode == MVX_MODE_FEATURES && spec->radii_type == MVX_RADII_CHANNEL_WISE;
+        if (chan_feat) {   // per-channel radius: one pass per channel (numpy/voxelizer.py:213-224)
+            for (int c = 0; c < C; ++c) {
+                vp.c_begin = c; vp.c_end = c + 1; vp.chan_radii = batch->radii;
+                MVX_CUDA_OK(launch_vox(batch->mode, 1, vp, binary, pl.nv, (unsigned)nblk, st));
+            }
+        } else {
+            vp.c_begin = 0; vp.c_end = batch->out_channels;
+            MVX_CUDA_OK(launch_vox(batch->mode, pick_chunk(batch->mode, batch->out_channels), vp, binary, pl.nv,
+                                   (unsigned)nblk, st));
+        }
+    }
+    prof_mark(st, 3);
+    if (g_prof.active && g_prof.calls < g_prof.max_calls) ++g_prof.calls;
+    return MVX_OK;
+}
+
+int mvx_profile_begin(int max_calls) {
+    if (g_prof.active) return fail(MVX_ERR_UNSUPPORTED, "a profile is already open on this thread");
+    if (max_calls < 1) return fail(MVX_ERR_BAD_SHAPE, "max_calls must be >= 1");
+    g_prof.ev = new cudaEvent_t[(size_t)max_calls * 4];
+    for (int i = 0; i < max_calls * 4; ++i) MVX_CUDA_OK(cudaEventCreate(&g_prof.ev[i]));
+    g_prof.max_calls = max_calls; g_prof.calls = 0; g_prof.active = true;
+    return MVX_OK;
+}
+
+int mvx_profile_end(double* ms_prep, double* ms_bin, double* ms_voxelize, int* num_calls) {
+    if (!g_prof.active) return fail(MVX_ERR_UNSUPPORTED, "no profile is open on this thread");
+    double t[3] = {0, 0, 0};
+    int rc = MVX_OK;
+    if (g_prof.calls > 0) {
+        if (cudaEventSynchronize(g_prof.ev[(g_prof.calls - 1) * 4 + 3]) != cudaSuccess) rc = MVX_ERR_CUDA;
+        for (int c = 0; c < g_prof.calls && rc == MVX_OK; ++c)
+            for (int k = 0; k < 3; ++k) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, g_prof.ev[c * 4 + k], g_prof.ev[c * 4 + k + 1]) != cudaSuccess) rc = MVX_ERR_CUDA;
+                t[k] += ms;
+            }
+    }
+    for (int i = 0; i < g_prof.max_calls * 4; ++i) cudaEventDestroy(g_prof.ev[i]);
+    delete[] g_prof.ev;
+    if (ms_prep) *ms_prep = t[0];
+    if (ms_bin) *ms_bin = t[1];
+    if (ms_voxelize) *ms_voxelize = t[2];
+    if (num_calls) *num_calls = g_prof.calls;
+    g_prof = Profile();
+    if (rc != MVX_OK) return fail(rc, "cudaEvent timing failed");
+    return MVX_OK;
+}
+
+int mvx_check_status(void* workspace, void* stream) {
+    if (!workspace) return fail(MVX_ERR_NULL_POINTER, "workspace is NULL");
+    int flags = 0;
+    MVX_CUDA_OK(cudaMemcpyAsync(&flags, workspace, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    MVX_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (flags & mvx::kFlagBadType) return fail(MVX_ERR_DEVICE_FLAG, "a type index is outside [0, num_channels)");
+    if (flags & mvx::kFlagRadiusOverMax) return fail(MVX_ERR_DEVICE_FLAG, "a radius exceeds max_radius");
+    return MVX_OK;
+}
+
+namespace {
+struct Staging { size_t off_offs, off_coords, off_centers, off_types, off_features, off_radii, total; };
+void plan_staging(const mvx_grid_spec* s, const mvx_batch* b, Staging* sg) {
+    const size_t N = (size_t)b->total_atoms, B = (size_t)b->num_mols;
+    const size_t C = b->mode == MVX_MODE_SINGLE ? 1 : (size_t)b->num_channels;
+    size_t off = 0;
+    sg->off_offs = off;     off += align_up((B + 1) * sizeof(int32_t));
+    sg->off_coords = off;   off += align_up(N * 3 * (b->coords_dtype == MVX_F64 ? 8 : 4));
+    sg->off_centers = off;  off += align_up(b->centers ? B * 3 * (b->centers_dtype == MVX_F64 ? 8 : 4) : 0);
+    sg->off_types = off;    off += align_up(b->mode == MVX_MODE_TYPES ? N * sizeof(int32_t) : 0);
+    sg->off_features = off; off += align_up(b->mode == MVX_MODE_FEATURES ? N * C * sizeof(float) : 0);
+    size_t nr = s->radii_type == MVX_RADII_ATOM_WISE ? N : (s->radii_type == MVX_RADII_CHANNEL_WISE ? C : 0);
+    sg->off_radii = off;    off += align_up(nr * sizeof(float));
+    sg->total = off;
+}
+}  // namespace
+
+int mvx_host_staging_bytes(const mvx_grid_spec* spec, const mvx_batch* batch, size_t* out_bytes) {
+    if (!out_bytes) return fail(MVX_ERR_NULL_POINTER, "out_bytes is NULL");
+    int rc = check_args(spec, batch);
+    if (rc != MVX_OK) return rc;
+    Staging sg;
+    plan_staging(spec, batch, &sg);
+    *out_bytes = sg.total;
+    return MVX_OK;
+}
+
+int mvx_voxelize_host(const mvx_grid_spec* spec, const mvx_batch* hb, float* out, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+    Plan pl;
+    int rc = make_plan(spec, hb, &pl);
+    if (rc != MVX_OK) return rc;
+    if (hb->num_mols == 0) return MVX_OK;
+    Staging sg;
+    plan_staging(spec, hb, &sg);
+    if (!workspace || workspace_bytes < pl.total + sg.total) return fail(MVX_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* dv = (char*)workspace + pl.total;
+    const size_t N = (size_t)hb->total_atoms, B = (size_t)hb->num_mols;
+    const size_t C = hb->mode == MVX_MODE_SINGLE ? 1 : (size_t)hb->num_channels;
+    mvx_batch db = *hb;
+    MVX_CUDA_OK(cudaMemcpyAsync(dv + sg.off_offs, hb->mol_offsets, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    db.mol_offsets = (const int32_t*)(dv + sg.off_offs);
+    if (N > 0) {
+        MVX_CUDA_OK(cudaMemcpyAsync(dv + sg.off_coords, hb->coords, N * 3 * (hb->coords_dtype == MVX_F64 ? 8 : 4),
+                                    cudaMemcpyHostToDevice, st));
+        db.coords = dv + sg.off_coords;
+    }
+    if (hb->centers) {
+        MVX_CUDA_OK(cudaMemcpyAsync(dv + sg.off_centers, hb->centers, B * 3 * (hb->centers_dtype == MVX_F64 ? 8 : 4),
+                                    cudaMemcpyHostToDevice, st));
+        db.centers = dv + sg.off_centers;
+    }
+    if (hb->mode == MVX_MODE_TYPES && N > 0) {
+        MVX_CUDA_OK(cudaMemcpyAsync(dv + sg.off_types, hb->types, N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        db.types = (const int32_t*)(dv + sg.off_types);
+    }
+    if (hb->mode == MVX_MODE_FEATURES && N > 0) {
+        MVX_CUDA_OK(cudaMemcpyAsync(dv + sg.off_features, hb->features, N * C * sizeof(float), cudaMemcpyHostToDevice, st));
+        db.features = (const float*)(dv + sg.off_features);
+    }
+    if (spec->radii_type != MVX_RADII_SCALAR && hb->radii) {
+        size_t nr = spec->radii_type == MVX_RADII_ATOM_WISE ? N : C;
+        if (nr > 0) {
+            MVX_CUDA_OK(cudaMemcpyAsync(dv + sg.off_radii, hb->radii, nr * sizeof(float), cudaMemcpyHostToDevice, st));
+            db.radii = (const float*)(dv + sg.off_radii);
+        }
+    }
+    rc = mvx_voxelize(spec, &db, out, workspace, pl.total, stream);
+    if (rc != MVX_OK) return rc;
+    return mvx_check_status(workspace, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,425 @@
+// mvx_kernels.cuh — sm_100a kernels of the voxelization hot path.
+//
+// Path restated (semantics only; the structure is new): reference molvoxel/voxelizer/numpy/voxelizer.py
+//   prologue + clip + block cull  :263-295, :481-527   -> mvx_prep_kernel   (one thread per atom, fp64)
+//   per-block atom lists          :496-527             -> mvx_bin_kernel    (CSR column lists, prefix sum)
+//   distance / density / channel accumulation  :531-560, :344-366, :194-236, :457-477
+//                                                      -> mvx_voxelize_kernel (gather, one write per voxel)
+//
+// Data layout in HBM
+//   out      (B, Cout, D, H, W) fp32, W contiguous (reference layout, numpy/voxelizer.py:60-70)
+//   AtomRec  40 B per atom: centred fp64 position, fp32 radius, cull "forbidden planes", z voxel range
+//   lists    uint32 atom ids per (molecule, 8x8 voxel column), ascending = the reference's atom order
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mvx {
+
+constexpr int kTile = 8;          // column footprint in x and y (voxels)
+constexpr int kThreads = 256;     // voxelize CTA size
+constexpr int kMaxCand = 128;     // candidates staged per round
+constexpr float kLog2e = 1.4426950408889634f;
+
+enum : int { kFlagBadType = 1, kFlagRadiusOverMax = 2 };
+
+struct __align__(8) AtomRec {
+    double px, py, pz;   // coords - center, fp64 (numpy/voxelizer.py:263-268)
+    float r;             // fp32 radius of the density kernel (max radius for channel-wise features)
+    int16_t fx, fy, fz;  // voxel plane the reference's block cull removes this atom from, or -1
+    int16_t zlo, zhi;    // conservative voxel z range
+    int16_t pad;
+};
+static_assert(sizeof(AtomRec) == 40, "AtomRec layout");
+
+struct Geo {
+    double res, half_width, res_half, lower, upper;
+    double clip_lo, clip_hi;     // scalar-form clip thresholds (lower - r, upper + r)
+    double size_scalar;          // scalar-form atom_size for the cull
+    double sigma;
+    int dim, bd, nb;             // nb == 1: exact mode (no cull)
+    int ncx;                     // columns per axis = ceil(dim / 8)
+    int scalar_form;             // clip/cull use the scalar thresholds
+    int radii_src;               // 0 scalar, 1 radii[n], 2 radii[types[n]], 3 channel-wise features
+    int cols_axis_max;           // capacity: columns an atom may span per axis
+    float r_scalar32;
+};
+
+struct PrepParams {
+    Geo g;
+    int mode, B, C;
+    int64_t N;
+    const int32_t* mol_offsets;
+    const void* coords; int coords_f64;
+    const void* centers; int centers_f64;
+    const int32_t* types;
+    const float* radii;
+    AtomRec* recs;
+    uint32_t* colrange;
+    int* status;
+};
+
+struct BinParams {
+    int B, ncol, ncx, maxcols;
+    const int32_t* mol_offsets;
+    const uint32_t* colrange;
+    uint2* bins;        // (start relative to the molecule's segment, count) per (mol, column)
+    uint32_t* lists;    // molecule m owns [mol_offsets[m]*maxcols, mol_offsets[m+1]*maxcols)
+};
+
+struct VoxParams {
+    double res, half_width, sigma;
+    float tau_lin, tau_quad;
+    int dim, ncx, ncol, nzc, tz;
+    int C, Cout, c_begin, c_end;
+    int maxcols;
+    const int32_t* mol_offsets;
+    const AtomRec* recs;
+    const uint2* bins;
+    const uint32_t* lists;
+    const int32_t* types;
+    const float* features;
+    const float* chan_radii;   // channel-wise features: kernel radius of channel c_begin
+    float* out;
+};
+
+// ---------------------------------------------------------------------------------------------
+// prep: one thread per atom.  Everything the reference decides per atom in fp64 is decided here,
+// with explicit round-to-nearest intrinsics so nvcc cannot contract a*b+c into an FMA.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double load_coord(const void* base, int is_f64, int64_t i) {
+    return is_f64 ? reinterpret_cast<const double*>(base)[i] : (double)reinterpret_cast<const float*>(base)[i];
+}
+
+__global__ void __launch_bounds__(256) mvx_prep_kernel(const PrepParams P) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= P.N) return;
+    const Geo& g = P.g;
+
+    int lo = 0, hi = P.B;   // offs[lo] <= n < offs[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if ((int64_t)P.mol_offsets[mid] <= n) lo = mid; else hi = mid;
+    }
+    const int mol = lo;
+
+    double p[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (P.centers == nullptr) {
+            p[k] = load_coord(P.coords, P.coords_f64, 3 * n + k);
+        } else if (!P.coords_f64 && !P.centers_f64) {   // fp32 - fp32 stays fp32 (numpy promotion)
+            float a = reinterpret_cast<const float*>(P.coords)[3 * n + k];
+            float b = reinterpret_cast<const float*>(P.centers)[3 * (int64_t)mol + k];
+            p[k] = (double)__fsub_rn(a, b);
+        } else {
+            p[k] = __dsub_rn(load_coord(P.coords, P.coords_f64, 3 * n + k),
+                             load_coord(P.centers, P.centers_f64, 3 * (int64_t)mol + k));
+        }
+    }
+
+    bool keep = true;
+    int type = 0;
+    if (P.mode == 1) {
+        type = P.types[n];
+        if (type < 0 || type >= P.C) { atomicOr(P.status, kFlagBadType); keep = false; type = 0; }
+    }
+    float r32;
+    if (g.radii_src == 0) r32 = g.r_scalar32;
+    else if (g.radii_src == 1) r32 = P.radii[n];
+    else if (g.radii_src == 2) r32 = P.radii[type];                // radii[types] (numpy/voxelizer.py:284-285)
+    else r32 = (float)g.size_scalar;
+    const double a = g.scalar_form ? g.size_scalar : (double)r32;  // "atom_size"
+
+    // global clip, strict (numpy/voxelizer.py:481-494)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (g.scalar_form) keep = keep && (p[k] > g.clip_lo) && (p[k] < g.clip_hi);
+        else keep = keep && (__dadd_rn(p[k], a) > g.lower) && (__dsub_rn(p[k], a) < g.upper);
+    }
+
+    // block cull (numpy/voxelizer.py:55, :504-511): block b >= 1 keeps the atom iff p > bounds[b-1] - a.
+    // The test is monotone in b; the first failing block's first voxel plane is the only place where a
+    // true hit is lost, so the cull reduces to one forbidden plane per axis.
+    int16_t forb[3] = {-1, -1, -1};
+    if (g.nb > 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            for (int b = 1; b < g.nb; ++b) {
+                double bound = __dadd_rn(__dsub_rn(__dmul_rn((double)(b * g.bd), g.res), g.half_width), g.res_half);
+                double thr = __dsub_rn(bound, a);
+                if (!(p[k] > thr)) { forb[k] = (int16_t)(b * g.bd); break; }
+            }
+        }
+    }
+
+    // conservative voxel ranges (speed only; 0.01 voxel of slack covers every rounding in play)
+    double reach = a > (double)r32 ? a : (double)r32;
+    reach = reach * (1.0 + 1e-6);
+    int v0[3], v1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double t0 = floor((p[k] - reach + g.half_width) / g.res - 0.01);
+        double t1 = ceil((p[k] + reach + g.half_width) / g.res + 0.01);
+        t0 = t0 < 0.0 ? 0.0 : t0;
+        t1 = t1 > (double)(g.dim - 1) ? (double)(g.dim - 1) : t1;
+        if (!(t0 <= t1)) keep = false;   // also catches NaN
+        v0[k] = keep ? (int)t0 : 0;
+        v1[k] = keep ? (int)t1 : 0;
+    }
+
+    uint32_t cr = 0x000000FFu;   // cx0 = 255 > cx1 = 0: overlaps nothing
+    if (keep) {
+        int cx0 = v0[0] / kTile, cx1 = v1[0] / kTile, cy0 = v0[1] / kTile, cy1 = v1[1] / kTile;
+        if (cx1 - cx0 + 1 > g.cols_axis_max) { atomicOr(P.status, kFlagRadiusOverMax); cx1 = cx0 + g.cols_axis_max - 1; }
+        if (cy1 - cy0 + 1 > g.cols_axis_max) { atomicOr(P.status, kFlagRadiusOverMax); cy1 = cy0 + g.cols_axis_max - 1; }
+        cr = (uint32_t)cx0 | ((uint32_t)cx1 << 8) | ((uint32_t)cy0 << 16) | ((uint32_t)cy1 << 24);
+    }
+    AtomRec rec;
+    rec.px = p[0]; rec.py = p[1]; rec.pz = p[2];
+    rec.r = r32;
+    rec.fx = forb[0]; rec.fy = forb[1]; rec.fz = forb[2];
+    rec.zlo = (int16_t)v0[2]; rec.zhi = (int16_t)v1[2];
+    rec.pad = 0;
+    P.recs[n] = rec;
+    P.colrange[n] = cr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bin: one CTA per molecule.  Warp w owns columns w, w+nwarps, ...; lanes stride over the atoms
+// 32 at a time and compact with ballot + popc, so each list keeps ascending atom order (the
+// reference's fp32 summation order, numpy/voxelizer.py:364-365) without atomics.
+// pass 1 counts, a CTA-wide exclusive prefix sum places the lists, pass 2 fills.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool col_overlaps(uint32_t cr, int cx, int cy) {
+    int cx0 = cr & 0xFF, cx1 = (cr >> 8) & 0xFF, cy0 = (cr >> 16) & 0xFF, cy1 = (cr >> 24) & 0xFF;
+    return cx >= cx0 && cx <= cx1 && cy >= cy0 && cy <= cy1;
+}
+
+__global__ void mvx_bin_kernel(const BinParams P) {
+    extern __shared__ uint32_t s_u32[];
+    uint32_t* s_cnt = s_u32;            // [ncol]
+    uint32_t* s_off = s_u32 + P.ncol;   // [ncol]
+    const int mol = blockIdx.x;
+    const int a0 = P.mol_offsets[mol], V = P.mol_offsets[mol + 1] - a0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t* cr = P.colrange + a0;
+    const int vpad = (V + 31) & ~31;
+
+    for (int col = warp; col < P.ncol; col += nwarps) {
+        const int cx = col / P.ncx, cy = col % P.ncx;
+        uint32_t cnt = 0;
+        for (int i = lane; i < vpad; i += 32) {
+            bool in = (i < V) && col_overlaps(cr[i], cx, cy);
+            cnt += __popc(__ballot_sync(0xffffffffu, in));
+        }
+        if (lane == 0) s_cnt[col] = cnt;
+    }
+    __syncthreads();
+    if (warp == 0) {   // exclusive scan over the columns, 32 at a time
+        uint32_t carry = 0;
+        for (int base = 0; base < P.ncol; base += 32) {
+            int i = base + lane;
+            uint32_t v = i < P.ncol ? s_cnt[i] : 0, x = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += y;
+            }
+            if (i < P.ncol) s_off[i] = carry + x - v;
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+    }
+    __syncthreads();
+    uint32_t* seg = P.lists + (size_t)a0 * (size_t)P.maxcols;
+    for (int col = warp; col < P.ncol; col += nwarps) {
+        const int cx = col / P.ncx, cy = col % P.ncx;
+        uint32_t pos = s_off[col];
+        if (s_cnt[col] != 0) {
+            for (int i = lane; i < vpad; i += 32) {
+                bool in = (i < V) && col_overlaps(cr[i], cx, cy);
+                uint32_t m = __ballot_sync(0xffffffffu, in);
+                if (in) seg[pos + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(a0 + i);
+                pos += __popc(m);
+            }
+        }
+        if (lane == 0) P.bins[(size_t)mol * P.ncol + col] = make_uint2(s_off[col], s_cnt[col]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// voxelize: one CTA per (molecule, 8x8 column, z chunk).  Each thread owns NV consecutive z voxels of
+// one (x, y) row for CH channels, gathers over the column's staged atoms in ascending order and
+// writes every output voxel exactly once (zeros included) with 128-bit stores along W.
+//
+// Cutoff decisions (the 0.135-high step of SURVEY.md hazard 3): fp32 d^2 from tile-relative
+// coordinates decides everything outside a tolerance band around r^2; inside the band the
+// reference's arithmetic is replayed exactly — fp64 sqrt((dx*dx+dy*dy)+dz*dz) with no FMA, rounded
+// to fp32, divided by the fp32 radius, compared with 1.0f (numpy/voxelizer.py:544-559 + scipy cdist).
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ bool exact_hit(const AtomRec* __restrict__ rec, float r32, int x, int y, int z,
+                                       double res, double half_width) {
+    double gx = __dsub_rn(__dmul_rn((double)x, res), half_width);
+    double gy = __dsub_rn(__dmul_rn((double)y, res), half_width);
+    double gz = __dsub_rn(__dmul_rn((double)z, res), half_width);
+    double dx = __dsub_rn(rec->px, gx), dy = __dsub_rn(rec->py, gy), dz = __dsub_rn(rec->pz, gz);
+    double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    float d32 = __double2float_rn(__dsqrt_rn(s));
+    return __fdiv_rn(d32, r32) <= 1.0f;
+}
+
+__device__ __forceinline__ void store_vox(float* p, const float (&v)[4]) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+}
+__device__ __forceinline__ void store_vox(float* p, const float (&v)[1]) { __stcs(p, v[0]); }
+
+template <int MODE, int CH, bool BINARY, int NV>
+__global__ void __launch_bounds__(kThreads) mvx_voxelize_kernel(const VoxParams P) {
+    __shared__ float4 sA[kMaxCand];   // rel x, rel y, rel z, r^2 + tau
+    __shared__ float4 sB[kMaxCand];   // r^2 - tau, gaussian coefficient, forbidden planes, type | radius
+    __shared__ int sIdx[kMaxCand];    // global atom id (exact recheck)
+    __shared__ float sF[MODE == 2 ? kMaxCand * CH : 1];
+
+    const int tid = threadIdx.x;
+    int t = blockIdx.x;
+    const int zc = t % P.nzc; t /= P.nzc;
+    const int col = t % P.ncol;
+    const int mol = t / P.ncol;
+    const int x0 = (col / P.ncx) * kTile, y0 = (col % P.ncx) * kTile, z0 = zc * P.tz;
+    const int D = P.dim;
+    const int z1 = min(D, z0 + P.tz);
+    const int lz = (z1 - z0 + NV - 1) / NV;   // thread items per (x, y) row
+    const int nitems = kTile * kTile * lz;
+    const size_t plane = (size_t)D * D * D;
+    float* out_mol = P.out + (size_t)mol * P.Cout * plane;
+
+    const uint2 bin = P.bins[(size_t)mol * P.ncol + col];
+    const int cnt = (int)bin.y;
+    const uint32_t* list = P.lists + (size_t)P.mol_offsets[mol] * (size_t)P.maxcols + bin.x;
+
+    if (cnt == 0) {   // empty column: pure zero fill
+        float zero[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) zero[k] = 0.f;
+        for (int ch = P.c_begin; ch < P.c_end; ++ch) {
+            for (int item = tid; item < nitems; item += kThreads) {
+                int row = item / lz, x = x0 + (row >> 3), y = y0 + (row & 7), z = z0 + (item - row * lz) * NV;
+                if (x < D && y < D) store_vox(out_mol + (size_t)ch * plane + ((size_t)x * D + y) * D + z, zero);
+            }
+        }
+        return;
+    }
+
+    const double ox0 = (double)x0 * P.res - P.half_width;
+    const double oy0 = (double)y0 * P.res - P.half_width;
+    const double oz0 = (double)z0 * P.res - P.half_width;
+    const bool single_round = cnt <= kMaxCand;
+    int staged_c0 = -1;
+
+    for (int c0 = P.c_begin; c0 < P.c_end; c0 += CH) {
+        for (int item0 = 0; item0 < nitems; item0 += kThreads) {
+            const int item = item0 + tid;
+            const int row = item / lz;
+            const int x = x0 + (row >> 3), y = y0 + (row & 7), z = z0 + (item - row * lz) * NV;
+            const bool valid = item < nitems && x < D && y < D;
+            const float ox = (float)((double)(x - x0) * P.res), oy = (float)((double)(y - y0) * P.res);
+            float oz[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) oz[k] = (float)((double)(z + k - z0) * P.res);
+            float acc[CH][NV];
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+#pragma unroll
+                for (int k = 0; k < NV; ++k) acc[c][k] = 0.f;
+
+            for (int r0 = 0; r0 < cnt; r0 += kMaxCand) {
+                const int nc = min(kMaxCand, cnt - r0);
+                if (!(single_round && staged_c0 == c0)) {
+                    __syncthreads();
+                    if (tid < nc) {
+                        const int n = (int)list[r0 + tid];
+                        const AtomRec rec = P.recs[n];
+                        float r = rec.r;
+                        if (MODE == 2 && P.chan_radii != nullptr) r = P.chan_radii[c0];
+                        const float r2 = r * r;
+                        const float tau = r * P.tau_lin + r2 * P.tau_quad;
+                        float r2hi = r2 + tau;
+                        if (rec.zhi < z0 || rec.zlo >= z1) r2hi = -1.f;   // outside this z chunk: never hits
+                        const int fx = rec.fx - x0, fy = rec.fy - y0, fz = rec.fz - z0;
+                        const uint32_t forb = (uint32_t)((rec.fx >= 0 && fx >= 0 && fx < kTile) ? fx : 0xFF) |
+                                              ((uint32_t)((rec.fy >= 0 && fy >= 0 && fy < kTile) ? fy : 0xFF) << 8) |
+                                              ((uint32_t)((rec.fz >= 0 && fz >= 0 && fz < 0xFFFF) ? fz : 0xFFFF) << 16);
+                        const double rs = (double)r * P.sigma;
+                        const float kc = (float)(-0.5 * 1.4426950408889634 / (rs * rs));
+                        sA[tid] = make_float4((float)(rec.px - ox0), (float)(rec.py - oy0), (float)(rec.pz - oz0), r2hi);
+                        sB[tid] = make_float4(r2 - tau, kc, __uint_as_float(forb),
+                                              MODE == 1 ? __int_as_float(P.types[n]) : r);
+                        sIdx[tid] = n;
+                    }
+                    if (MODE == 2) {
+                        for (int i = tid; i < nc * CH; i += kThreads) {
+                            int j = i / CH, c = i - j * CH;
+                            int n = (int)list[r0 + j];
+                            sF[i] = (c0 + c < P.C) ? P.features[(size_t)n * P.C + c0 + c] : 0.f;
+                        }
+                    }
+                    __syncthreads();
+                    staged_c0 = c0;
+                }
+                if (!valid) continue;
+                for (int j = 0; j < nc; ++j) {
+                    const float4 A = sA[j];
+                    const float dx = A.x - ox, dy = A.y - oy;
+                    const float dxy = dx * dx + dy * dy;
+                    if (dxy > A.w) continue;
+                    const float4 Bv = sB[j];
+                    const uint32_t forb = __float_as_uint(Bv.z);
+                    if ((int)(forb & 0xFF) == x - x0 || (int)((forb >> 8) & 0xFF) == y - y0) continue;
+                    const int fz = (int)(forb >> 16);
+                    float w[NV];
+                    bool any = false;
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) {
+                        const float dz = A.z - oz[k];
+                        const float s = dxy + dz * dz;
+                        bool hit = s < Bv.x;
+                        if (!hit && s <= A.w) {
+                            float r32 = (MODE == 1) ? P.recs[sIdx[j]].r : Bv.w;
+                            hit = exact_hit(P.recs + sIdx[j], r32, x, y, z + k, P.res, P.half_width);
+                        }
+                        if (z + k - z0 == fz) hit = false;
+                        w[k] = hit ? (BINARY ? 1.0f : exp2f(s * Bv.y)) : 0.f;
+                        any = any || hit;
+                    }
+                    if (!any) continue;
+                    if (MODE == 0) {
+#pragma unroll
+                        for (int k = 0; k < NV; ++k) acc[0][k] += w[k];
+                    } else if (MODE == 1) {
+                        const int ct = __float_as_int(Bv.w) - c0;
+#pragma unroll
+                        for (int c = 0; c < CH; ++c)
+#pragma unroll
+                            for (int k = 0; k < NV; ++k) acc[c][k] += (ct == c) ? w[k] : 0.f;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) {
+                            const float f = sF[j * CH + c];
+#pragma unroll
+                            for (int k = 0; k < NV; ++k) acc[c][k] = fmaf(f, w[k], acc[c][k]);
+                        }
+                    }
+                }
+            }
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int ch = c0 + c;
+                    if (ch < P.c_end) store_vox(out_mol + (size_t)ch * plane + ((size_t)x * D + y) * D + z, acc[c]);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace mvx

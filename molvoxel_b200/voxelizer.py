@@ -1,0 +1,419 @@
+"""Host-side mirror of the reference Voxelizer interface for the `library="b200"` backend.
+
+Mirrors reference molvoxel/voxelizer/base/voxelizer.py:9-176 (contract) and the torch flavour's
+device handling (molvoxel/voxelizer/torch/voxelizer.py:59-88, :569-582); argument checks repeat the
+numpy backend's asserts (molvoxel/voxelizer/numpy/voxelizer.py:171-192, :317-342, :438-455) with the
+same messages.  All compute happens in libmolvoxel_b200.so (hand-written sm_100a kernels) through
+the C ABI in include/molvoxel_b200.h; torch is used for device memory and streams only.  There is
+no CPU path: without a CUDA device every forward_* raises RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .transform import RandomTransform, random_transform_params, apply_transform
+
+
+def _norm(x):
+    """Lists/tuples become numpy arrays; tensors, arrays, scalars and None pass through."""
+    if x is None or isinstance(x, (torch.Tensor, np.ndarray)) or np.isscalar(x):
+        return x
+    return np.asarray(x)
+
+
+def _is_scalar(x) -> bool:
+    if isinstance(x, torch.Tensor):
+        return x.ndim == 0
+    return np.isscalar(x) or (isinstance(x, np.ndarray) and x.ndim == 0)
+
+
+class Voxelizer:
+    LIB = "B200"
+    transform_class = RandomTransform
+    RADII_TYPE_LIST = ["scalar", "channel-wise", "atom-wise"]
+    DENSITY_TYPE_LIST = ["gaussian", "binary"]
+
+    def __init__(
+        self,
+        resolution: float = 0.5,
+        dimension: int = 64,
+        radii_type: str = "scalar",
+        density_type: str = "gaussian",
+        device: str | torch.device = "cuda",
+        blockdim: int | None = None,
+        **kwargs,
+    ):
+        assert radii_type in self.RADII_TYPE_LIST
+        assert density_type in self.DENSITY_TYPE_LIST
+        self._resolution = resolution
+        self._dimension = dimension
+        self._width = resolution * (dimension - 1)
+        self._radii_type = radii_type
+        self._density_type = density_type
+        self.upper_bound = self.width / 2.0
+        self.lower_bound = -1 * self.upper_bound
+        self._spatial_dimension = (dimension, dimension, dimension)
+        self._sigma = kwargs.get("sigma", 0.5)
+        # `blockdim` keeps the reference meaning: the block size whose half-voxel cull the result must
+        # reproduce (numpy default 8).  blockdim >= dimension gives the exact mathematics.
+        self.blockdim = 8 if blockdim is None else int(blockdim)
+        self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None and torch.cuda.is_available():
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._ws = None
+        _lib.lib()   # fail loudly here if the CUDA library cannot be built/loaded
+
+    # ---- properties of the reference contract (base/voxelizer.py:40-97) ----
+    @property
+    def radii_type(self) -> str:
+        return self._radii_type
+
+    @radii_type.setter
+    def radii_type(self, radii_type: str):
+        assert radii_type in self.RADII_TYPE_LIST
+        self._radii_type = radii_type
+
+    @property
+    def is_radii_type_scalar(self):
+        return self._radii_type == "scalar"
+
+    @property
+    def is_radii_type_channel_wise(self):
+        return self._radii_type == "channel-wise"
+
+    @property
+    def is_radii_type_atom_wise(self):
+        return self._radii_type == "atom-wise"
+
+    @property
+    def density_type(self) -> str:
+        return self._density_type
+
+    @density_type.setter
+    def density_type(self, density_type: str):
+        assert density_type in self.DENSITY_TYPE_LIST
+        self._density_type = density_type
+        if density_type == "gaussian":
+            self._sigma = 0.5   # the reference setter cannot receive sigma either (base/voxelizer.py:65-70)
+
+    @property
+    def is_density_type_binary(self):
+        return self._density_type == "binary"
+
+    @property
+    def is_density_type_gaussian(self):
+        return self._density_type == "gaussian"
+
+    def grid_dimension(self, num_channels: int):
+        return (num_channels, self._dimension, self._dimension, self._dimension)
+
+    @property
+    def spatial_dimension(self):
+        return self._spatial_dimension
+
+    @property
+    def resolution(self) -> float:
+        return self._resolution
+
+    @property
+    def dimension(self) -> int:
+        return self._dimension
+
+    @property
+    def width(self) -> float:
+        return self._width
+
+    # ---- device handling (torch/voxelizer.py:73-88; returns self even when unchanged) ----
+    def to(self, device, update_blockdim: bool = True, blockdim: int | None = None):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("molvoxel_b200 has no CPU path; device must be a CUDA device")
+        if device.index is None and torch.cuda.is_available():
+            device = torch.device("cuda", torch.cuda.current_device())
+        if device != self.device:
+            self.device = device
+            self._ws = None
+        if blockdim is not None:
+            self.blockdim = int(blockdim)
+        return self
+
+    def cuda(self, update_blockdim: bool = True, blockdim: int | None = None):
+        return self.to("cuda", update_blockdim, blockdim)
+
+    def cpu(self, *args, **kwargs):
+        raise RuntimeError("molvoxel_b200 has no CPU path")
+
+    def get_empty_grid(self, num_channels: int, batch_size: int | None = None, init_zero: bool = False):
+        shape = self.grid_dimension(num_channels)
+        if batch_size is not None:
+            shape = (batch_size,) + shape
+        fn = torch.zeros if init_zero else torch.empty
+        return fn(shape, dtype=torch.float32, device=self.device)
+
+    def asarray(self, array, obj: str):
+        """torch/voxelizer.py:569-582; coords/center keep fp64 (the numpy oracle's centring precision)."""
+        if obj in ("coords", "center"):
+            dt = torch.float64
+        elif obj in ("features", "radii"):
+            dt = torch.float32
+        elif obj == "types":
+            dt = torch.int32
+        else:
+            raise ValueError("obj should be ['coords', 'center', 'radii', types', 'features']")
+        if isinstance(array, np.ndarray):
+            return torch.from_numpy(np.ascontiguousarray(array)).to(self.device, dt)
+        return torch.as_tensor(array).to(self.device, dt)
+
+    # ---- reference forward API ----
+    def forward(self, coords, center, channels, radii, random_translation: float = 0.0,
+                random_rotation: bool = False, out_grid=None):
+        if channels is None:
+            return self.forward_single(coords, center, radii, random_translation, random_rotation, out_grid)
+        elif np.ndim(channels) == 1 if not isinstance(channels, torch.Tensor) else channels.ndim == 1:
+            return self.forward_types(coords, center, channels, radii, random_translation, random_rotation, out_grid)
+        else:
+            return self.forward_features(coords, center, channels, radii, random_translation, random_rotation, out_grid)
+
+    __call__ = forward
+
+    def forward_types(self, coords, center, types, radii, random_translation: float = 0.0,
+                      random_rotation: bool = False, out_grid=None):
+        """(V,3), (3,)|None, (V,), scalar|(C,)|(V,) -> (C,D,H,W); numpy/voxelizer.py:240-315."""
+        coords, center, types, radii = _norm(coords), _norm(center), _norm(types), _norm(radii)
+        V = int(coords.shape[0])
+        offs = [0, V]
+        centers = None if center is None else center.reshape(1, 3)
+        if self.is_radii_type_channel_wise and not _is_scalar(radii):
+            C = int(radii.shape[0])
+            Cmax = None
+        else:
+            C = None
+            Cmax = True
+        out = self._forward_batch("types", coords, offs, centers, types, radii, C, random_translation,
+                                  random_rotation, None if out_grid is None else out_grid.unsqueeze(0),
+                                  infer_types_channels=Cmax is True)
+        return out_grid if out_grid is not None else out[0]
+
+    def forward_features(self, coords, center, features, radii, random_translation: float = 0.0,
+                         random_rotation: bool = False, out_grid=None):
+        """(V,3), (3,)|None, (V,C), scalar|(C,)|(V,) -> (C,D,H,W); numpy/voxelizer.py:97-169."""
+        coords, center, features, radii = _norm(coords), _norm(center), _norm(features), _norm(radii)
+        V = int(coords.shape[0])
+        centers = None if center is None else center.reshape(1, 3)
+        assert features.ndim == 2, f"atom features does not match dimension: {tuple(features.shape)} vs {(V, '*')}"
+        out = self._forward_batch("features", coords, [0, V], centers, features, radii, int(features.shape[1]),
+                                  random_translation, random_rotation,
+                                  None if out_grid is None else out_grid.unsqueeze(0))
+        return out_grid if out_grid is not None else out[0]
+
+    def forward_single(self, coords, center, radii, random_translation: float = 0.0,
+                       random_rotation: bool = False, out_grid=None):
+        """(V,3), (3,)|None, scalar|(V,) -> (1,D,H,W); numpy/voxelizer.py:370-436."""
+        coords, center, radii = _norm(coords), _norm(center), _norm(radii)
+        V = int(coords.shape[0])
+        centers = None if center is None else center.reshape(1, 3)
+        out = self._forward_batch("single", coords, [0, V], centers, None, radii, 1, random_translation,
+                                  random_rotation, None if out_grid is None else out_grid.unsqueeze(0))
+        return out_grid if out_grid is not None else out[0]
+
+    # ---- batched driver (new, additive; per-molecule semantics = B independent reference calls) ----
+    def forward_types_batch(self, coords, mol_offsets, centers, types, radii, num_channels,
+                            random_translation: float = 0.0, random_rotation: bool = False, out=None):
+        return self._forward_batch("types", coords, mol_offsets, centers, types, radii, int(num_channels),
+                                   random_translation, random_rotation, out)
+
+    def forward_features_batch(self, coords, mol_offsets, centers, features, radii,
+                               random_translation: float = 0.0, random_rotation: bool = False, out=None):
+        return self._forward_batch("features", coords, mol_offsets, centers, features, radii,
+                                   int(features.shape[1]), random_translation, random_rotation, out)
+
+    def forward_single_batch(self, coords, mol_offsets, centers, radii,
+                             random_translation: float = 0.0, random_rotation: bool = False, out=None):
+        return self._forward_batch("single", coords, mol_offsets, centers, None, radii, 1,
+                                   random_translation, random_rotation, out)
+
+    # ---- implementation ----
+    def _spec(self):
+        return _lib.GridSpec(float(self._resolution), int(self._dimension), _lib.DENSITY[self._density_type],
+                             float(self._sigma), _lib.RADII[self._radii_type], int(self.blockdim))
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _check_radii(self, mode, radii, V, C):
+        if mode == "single":
+            assert not self.is_radii_type_channel_wise, "Channel-Wise Radii Type is not supported"
+        if self.is_radii_type_scalar:
+            assert _is_scalar(radii), "the radii type of voxelizer is `scalar`, radii should be scalar"
+        elif self.is_radii_type_channel_wise:
+            assert not _is_scalar(radii), f"the radii type of voxelizer is `channel-wise`, radii should be Array[{C},]"
+            assert tuple(radii.shape) == (C,), \
+                f"radii does not match dimension (number of channels,): {tuple(radii.shape)} vs {(C,)}"
+        else:
+            assert not _is_scalar(radii), f"the radii type of voxelizer is `atom-wise`, radii should be Array[{V},]"
+            assert tuple(radii.shape) == (V,), \
+                f"radii does not match dimension (number of atoms,): {tuple(radii.shape)} vs {(V,)}"
+
+    def _forward_batch(self, mode, coords, mol_offsets, centers, channels, radii, C, random_translation,
+                       random_rotation, out, infer_types_channels=False, max_radius=None):
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("molvoxel_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        coords, centers, channels, radii = _norm(coords), _norm(centers), _norm(channels), _norm(radii)
+        on_device = isinstance(coords, torch.Tensor) and coords.is_cuda
+        D = self._dimension
+        N = int(coords.shape[0])
+        assert coords.ndim == 2 and coords.shape[1] == 3, f"coords should be (V, 3): {tuple(coords.shape)}"
+
+        # molecule offsets
+        if isinstance(mol_offsets, torch.Tensor):
+            B = int(mol_offsets.shape[0]) - 1
+        else:
+            mol_offsets = np.ascontiguousarray(np.asarray(mol_offsets), dtype=np.int32)
+            B = int(mol_offsets.shape[0]) - 1
+            assert int(mol_offsets[0]) == 0 and int(mol_offsets[-1]) == N, "mol_offsets must span [0, N]"
+
+        # channel bookkeeping + the reference's argument checks
+        if mode == "types":
+            assert tuple(channels.shape) == (N,), f"types does not match dimension: {tuple(channels.shape)} vs {(N,)}"
+            if infer_types_channels:
+                if out is not None and on_device:
+                    C = int(out.shape[1])        # no host sync: the device validates types < C
+                else:
+                    tmax = channels.max()        # V == 0 raises like np.max on an empty array
+                    C = int(tmax) + 1
+            self._check_radii(mode, radii, N, C)
+        elif mode == "features":
+            assert channels.shape[0] == N, f"atom features does not match number of atoms: {channels.shape[0]} vs {N}"
+            self._check_radii(mode, radii, N, C)
+        else:
+            self._check_radii(mode, radii, N, C)
+
+        if out is not None:
+            assert isinstance(out, torch.Tensor) and out.is_cuda and out.dtype == torch.float32 and out.is_contiguous(), \
+                "out_grid must be a contiguous float32 CUDA tensor"
+            if mode == "types":
+                assert out.shape[1] >= C, f"Output channel is less than number of types: {out.shape[1]} < {C}"
+                assert tuple(out.shape[2:]) == (D, D, D), \
+                    f'Output grid dimension incorrect: {tuple(out.shape[1:])} vs {("*", D, D, D)}'
+            elif mode == "features":
+                assert tuple(out.shape[1:]) == (C, D, D, D), \
+                    f"Output grid dimension incorrect: {tuple(out.shape[1:])} vs {(C, D, D, D)}"
+            else:
+                assert out.shape[1] == 1, "Output channel should be 1"
+                assert tuple(out.shape[2:]) == (D, D, D), \
+                    f'Output grid dimension incorrect: {tuple(out.shape[1:])} vs {("*", D, D, D)}'
+            assert out.shape[0] == B
+            out_channels = int(out.shape[1])
+        else:
+            out_channels = C
+            out = torch.empty((B, out_channels, D, D, D), dtype=torch.float32, device=self.device)
+
+        # centring stays inside the kernel (fp64 or numpy's fp32-fp32 promotion); the optional random
+        # rigid transform is applied to centred coordinates first, like the reference (numpy/voxelizer.py:263-265)
+        if (random_translation is not None and random_translation > 0.0) or random_rotation:
+            coords, centers = apply_transform(coords, mol_offsets, centers,
+                                              random_transform_params(B, random_translation, random_rotation))
+
+        keep = []   # keeps converted arrays alive until the call returns
+
+        def dev(t, dt):
+            t = t.to(self.device, dt).contiguous()
+            keep.append(t)
+            return t
+
+        def host(a, dt=None):
+            a = np.ascontiguousarray(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a), dtype=dt)
+            keep.append(a)
+            return a
+
+        b = _lib.Batch()
+        b.mode, b.num_mols, b.total_atoms = _lib.MODE[mode], B, N
+        b.num_channels, b.out_channels = C, out_channels
+        b.radius, b.max_radius = 0.0, 0.0
+
+        def fdtype_of(x):
+            if isinstance(x, torch.Tensor):
+                return torch.float32 if x.dtype == torch.float32 else torch.float64
+            return np.float32 if x.dtype == np.float32 else np.float64
+
+        if on_device:
+            ptr = lambda t: ctypes.c_void_p(t.data_ptr())   # noqa: E731
+            offs_t = mol_offsets if isinstance(mol_offsets, torch.Tensor) else torch.from_numpy(mol_offsets)
+            b.mol_offsets = ptr(dev(offs_t, torch.int32))
+            cdt = fdtype_of(coords)
+            b.coords, b.coords_dtype = ptr(dev(coords, cdt)), int(cdt == torch.float64)
+            if centers is not None:
+                centers = torch.as_tensor(centers) if not isinstance(centers, torch.Tensor) else centers
+                zdt = fdtype_of(centers)
+                b.centers, b.centers_dtype = ptr(dev(centers.reshape(B, 3), zdt)), int(zdt == torch.float64)
+            if mode == "types":
+                b.types = ptr(dev(torch.as_tensor(channels), torch.int32))
+            elif mode == "features":
+                b.features = ptr(dev(torch.as_tensor(channels), torch.float32))
+            if self.is_radii_type_scalar:
+                b.radius = float(radii)
+            else:
+                r = dev(torch.as_tensor(radii), torch.float32)
+                b.radii = ptr(r)
+                b.max_radius = float(max_radius) if max_radius is not None else (float(r.max()) if r.numel() else 1.0)
+        else:
+            ptr = lambda a: ctypes.c_void_p(a.ctypes.data)   # noqa: E731
+            b.mol_offsets = ptr(host(mol_offsets, np.int32))
+            coords = coords.detach().cpu().numpy() if isinstance(coords, torch.Tensor) else np.asarray(coords)
+            cdt = fdtype_of(coords)
+            b.coords, b.coords_dtype = ptr(host(coords, cdt)), int(cdt == np.float64)
+            if centers is not None:
+                centers = centers.detach().cpu().numpy() if isinstance(centers, torch.Tensor) else np.asarray(centers)
+                zdt = fdtype_of(centers)
+                b.centers, b.centers_dtype = ptr(host(centers.reshape(B, 3), zdt)), int(zdt == np.float64)
+            if mode == "types":
+                t = channels.detach().cpu().numpy() if isinstance(channels, torch.Tensor) else np.asarray(channels)
+                b.types = ptr(host(t.astype(np.int16), np.int32))   # the reference narrows to int16 (:269)
+            elif mode == "features":
+                b.features = ptr(host(channels, np.float32))
+            if self.is_radii_type_scalar:
+                b.radius = float(radii)
+            else:
+                r = host(radii, np.float32)
+                b.radii = ptr(r)
+                b.max_radius = float(max_radius) if max_radius is not None else (float(r.max()) if r.size else 1.0)
+
+        L = _lib.lib()
+        spec = self._spec()
+        need = ctypes.c_size_t(0)
+        _lib.raise_for_status(L.mvx_workspace_bytes(ctypes.byref(spec), ctypes.byref(b), ctypes.byref(need)))
+        total = need.value
+        if not on_device:
+            stg = ctypes.c_size_t(0)
+            _lib.raise_for_status(L.mvx_host_staging_bytes(ctypes.byref(spec), ctypes.byref(b), ctypes.byref(stg)))
+            total += stg.value
+        ws = self._workspace(total)
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+        ws_bytes = ws.numel() - (ws_ptr - ws.data_ptr())
+        with torch.cuda.device(self.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            fn = L.mvx_voxelize if on_device else L.mvx_voxelize_host
+            rc = fn(ctypes.byref(spec), ctypes.byref(b), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws_ptr),
+                    ctypes.c_size_t(ws_bytes), stream)
+        _lib.raise_for_status(rc)
+        if on_device:
+            for t in keep:   # inputs converted on the fly must outlive the asynchronous kernels
+                if isinstance(t, torch.Tensor):
+                    t.record_stream(torch.cuda.current_stream(self.device))
+        return out
+
+    def check_status(self):
+        """Synchronise and raise if the last device-path call flagged bad types / radii (device-side validation)."""
+        if self._ws is None:
+            return
+        ws_ptr = (self._ws.data_ptr() + 255) // 256 * 256
+        with torch.cuda.device(self.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.raise_for_status(_lib.lib().mvx_check_status(ctypes.c_void_p(ws_ptr), stream))

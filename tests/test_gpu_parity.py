@@ -1,0 +1,215 @@
+"""Parity of the CUDA path (through the C ABI) against golden vectors and the oracle.  Needs a B200."""
+import numpy as np
+import pytest
+import torch
+
+import molvoxel_b200 as mv
+from oracle import OracleVoxelizer, oracle_forward_batch
+from tests.helpers import GoldenCase, golden_names, ligand_batch
+
+pytestmark = pytest.mark.gpu
+
+GAUSS_TOL = 1e-5   # north_star: max-abs <= 1e-5 relative to peak density; binary: bit-exact
+
+
+def _vox(cfg, **kw):
+    return mv.create_voxelizer(cfg["resolution"], cfg["dimension"], cfg["radii_type"], cfg["density_type"],
+                               library="b200", blockdim=cfg.get("blockdim"), sigma=cfg.get("sigma", 0.5), **kw)
+
+
+def _run_case(vox, g, device_inputs):
+    cfg = g.cfg
+    conv = (lambda a, what: None if a is None else vox.asarray(a, what)) if device_inputs else (lambda a, what: a)
+    coords, center = g.coords, g.center
+    if device_inputs:   # keep the fixture's dtypes (fp32 coords exercise numpy's fp32 centring)
+        coords = torch.from_numpy(g.coords).cuda()
+        center = None if g.center is None else torch.from_numpy(g.center).cuda()
+    radii = g.radii if np.isscalar(g.radii) else conv(g.radii, "radii")
+    if cfg["mode"] == "types":
+        return vox.forward_types(coords, center, conv(g.channels, "types"), radii)
+    if cfg["mode"] == "features":
+        return vox.forward_features(coords, center, conv(g.channels, "features"), radii)
+    return vox.forward_single(coords, center, radii)
+
+
+@pytest.mark.parametrize("device_inputs", [False, True], ids=["host_inputs", "device_inputs"])
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_matches_reference_golden(name, device_inputs):
+    g = GoldenCase(name)
+    vox = _vox(g.cfg)
+    out = _run_case(vox, g, device_inputs)
+    assert out.is_cuda and out.dtype == torch.float32
+    vox.check_status()
+    g.check(out.cpu().numpy(), gauss_tol=GAUSS_TOL)
+
+
+def _compare(got, ref, binary_exact, tol=GAUSS_TOL):
+    if binary_exact:
+        assert np.array_equal(got, ref), f"{(got != ref).sum()} voxels differ"
+        return
+    assert np.array_equal(got != 0, ref != 0), f"support differs in {((got != 0) != (ref != 0)).sum()} voxels"
+    peak = max(1.0, float(np.abs(ref).max()))
+    err = float(np.abs(got - ref).max())
+    assert err <= tol * peak, f"max-abs {err} vs {tol * peak}"
+
+
+@pytest.mark.parametrize("density", ["binary", "gaussian"])
+def test_cfg3_ligand_batch_types_vs_oracle(density):
+    """BASELINE cfg 3 shape: 64^3, ~50-atom ligands, 4 types; binary must be bit-exact per molecule."""
+    rng = np.random.default_rng(3)
+    B = 96
+    offs, coords, types = ligand_batch(rng, B, 4)
+    vox = mv.create_voxelizer(0.5, 64, "scalar", density, library="b200")
+    out = vox.forward_types_batch(coords, offs, None, types, 1.0, 4).cpu().numpy()
+    ref = oracle_forward_batch(0.5, 64, "scalar", density, 0.5, 8, "types", offs, coords, None, types, None, 4, 1.0,
+                               num_threads=8)
+    _compare(out, ref, density == "binary")
+    # batch element == single call, bitwise
+    for m in (0, B // 2, B - 1):
+        a, b = offs[m], offs[m + 1]
+        one = vox.forward_types(coords[a:b], None, types[a:b], 1.0,
+                                out_grid=vox.get_empty_grid(4)).cpu().numpy()
+        assert np.array_equal(one, out[m])
+
+
+def test_cfg4_nine_channel_ligands_vs_oracle():
+    rng = np.random.default_rng(4)
+    B = 48
+    offs, coords, types = ligand_batch(rng, B, 9)
+    centers = rng.normal(scale=0.3, size=(B, 3))
+    vox = mv.create_voxelizer(0.5, 64, "scalar", "gaussian", library="b200")
+    out = vox.forward_types_batch(torch.from_numpy(coords).cuda(), torch.from_numpy(offs).cuda(),
+                                  torch.from_numpy(centers).cuda(), torch.from_numpy(types).cuda(), 1.0, 9)
+    vox.check_status()
+    ref = oracle_forward_batch(0.5, 64, "scalar", "gaussian", 0.5, 8, "types", offs, coords, centers, types, None, 9,
+                               1.0, num_threads=8)
+    _compare(out.cpu().numpy(), ref, False)
+
+
+@pytest.mark.parametrize("dense", [False, True], ids=["sparse_feats", "dense_feats"])
+def test_cfg2_pocket_features_vs_oracle(dense):
+    """BASELINE cfg 2 shape: ~2,000 atoms, C=16, 48^3 (batch shortened so the oracle finishes in seconds)."""
+    rng = np.random.default_rng(2)
+    B, V, C = 4, 2000, 16
+    half = 0.5 * 47 / 2
+    coords = rng.uniform(-half, half, size=(B * V, 3)).astype(np.float32).astype(np.float64)
+    offs = np.arange(B + 1, dtype=np.int32) * V
+    if dense:
+        feats = rng.uniform(0, 1, size=(B * V, C)).astype(np.float32)
+    else:
+        feats = np.zeros((B * V, C), dtype=np.float32)
+        feats[np.arange(B * V), rng.integers(0, 8, size=B * V)] = 1.0
+        feats[:, 8:] = (rng.uniform(size=(B * V, 8)) < 0.25).astype(np.float32)
+    vox = mv.create_voxelizer(0.5, 48, "scalar", "gaussian", library="b200")
+    out = vox.forward_features_batch(coords, offs, np.zeros((B, 3)), feats, 1.0).cpu().numpy()
+    ref = oracle_forward_batch(0.5, 48, "scalar", "gaussian", 0.5, 8, "features", offs, coords, np.zeros((B, 3)), None,
+                               feats, C, 1.0, num_threads=8)
+    _compare(out, ref, False, tol=GAUSS_TOL)
+
+
+def test_cfg5_large_complex_atomwise_vs_oracle():
+    """BASELINE cfg 5 shape: 96^3, res 0.375, C=32, atom-wise radii (atom count shortened for the oracle)."""
+    rng = np.random.default_rng(5)
+    V, C = 4000, 32
+    half = 0.375 * 95 / 2
+    coords = rng.uniform(-half - 1, half + 1, size=(V, 3))
+    feats = rng.uniform(0, 1, size=(V, C)).astype(np.float32)
+    radii = rng.uniform(1.0, 2.0, size=V).astype(np.float32)
+    vox = mv.create_voxelizer(0.375, 96, "atom-wise", "gaussian", library="b200")
+    out = vox.forward_features(coords, np.zeros(3), feats, radii).cpu().numpy()
+    ref = OracleVoxelizer(0.375, 96, "atom-wise", "gaussian").forward_features(coords, np.zeros(3), feats, radii)
+    _compare(out, ref, False, tol=GAUSS_TOL)
+
+
+def test_exact_mode_matches_oracle_blockdim_dim():
+    rng = np.random.default_rng(11)
+    V = 1500
+    coords = rng.uniform(-13, 13, size=(V, 3))
+    types = rng.integers(0, 4, size=V)
+    vox = mv.create_voxelizer(0.5, 48, "scalar", "binary", library="b200", blockdim=48)
+    out = vox.forward_types(coords, None, types, 1.0).cpu().numpy()
+    ref = OracleVoxelizer(0.5, 48, "scalar", "binary", blockdim=48).forward_types(coords, None, types, 1.0)
+    assert np.array_equal(out, ref)
+    compat = mv.create_voxelizer(0.5, 48, "scalar", "binary", library="b200").forward_types(coords, None, types, 1.0).cpu().numpy()
+    assert (compat <= out).all()                      # the cull only ever loses hits ...
+    xs = np.unique(np.argwhere(compat != out)[:, 1:], axis=0)
+    assert ((xs % 8 == 0) & (xs > 0)).any(axis=1).all()   # ... on first planes of non-first blocks
+
+
+def test_types_equals_onehot_features():
+    """The reference's own cross-path invariant (test/test_time_numpy.py:67-69), at full 64^3 size."""
+    rng = np.random.default_rng(7)
+    offs, coords, types = ligand_batch(rng, 16, 9)
+    vox = mv.create_voxelizer(0.5, 64, "scalar", "gaussian", library="b200")
+    a = vox.forward_types_batch(coords, offs, None, types, 1.0, 9)
+    onehot = np.eye(9, dtype=np.float32)[types]
+    b = vox.forward_features_batch(coords, offs, None, onehot, 1.0)
+    assert torch.equal(a, b)
+    s = vox.forward_single_batch(coords, offs, None, 1.0)
+    assert float((a.sum(1, keepdim=True) - s).abs().max()) <= 1e-5
+
+
+def test_size_independent_properties_full_batch():
+    """Full cfg 3 batch (1,024 ligands, 64^3): properties that need no oracle run."""
+    rng = np.random.default_rng(33)
+    B = 1024
+    offs, coords, types = ligand_batch(rng, B, 4)
+    vox = mv.create_voxelizer(0.5, 64, "scalar", "binary", library="b200")
+    out = vox.forward_types_batch(coords, offs, None, types, 1.0, 4)
+    # binary grids hold small non-negative integers (overlap counts)
+    assert bool((out == out.round()).all()) and float(out.min()) == 0.0
+    # translating coords and centre by the same fp32-exact vector is a no-op
+    shift = np.array([4.0, -2.5, 8.25])
+    out2 = vox.forward_types_batch(coords + shift, offs, np.tile(shift, (B, 1)), types, 1.0, 4)
+    assert torch.equal(out, out2)
+    # idempotent / deterministic: same call, same bits
+    assert torch.equal(out, vox.forward_types_batch(coords, offs, None, types, 1.0, 4))
+    # permuting molecules permutes grids
+    m = 17
+    a, b = offs[m], offs[m + 1]
+    one = vox.forward_types(coords[a:b], None, types[a:b], 1.0, out_grid=vox.get_empty_grid(4))
+    assert torch.equal(one, out[m])
+    # every atom inside the box hits at least its nearest voxel: per-molecule mass >= atom count
+    mass = out.sum(dim=(1, 2, 3, 4)).cpu().numpy()
+    assert (mass >= (offs[1:] - offs[:-1])).all()
+
+
+def test_edge_cases():
+    vox = mv.create_voxelizer(0.5, 32, "scalar", "gaussian", library="b200")
+    # V = 0: forward_single works, forward_types raises ValueError like np.max on empty
+    z = vox.forward_single(np.zeros((0, 3)), None, 1.0)
+    assert z.shape == (1, 32, 32, 32) and float(z.abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        vox.forward_types(np.zeros((0, 3)), None, np.zeros((0,), dtype=np.int16), 1.0)
+    # all atoms outside -> all-zero grid; atom exactly r outside is clipped (strict inequality)
+    far = np.array([[100.0, 0, 0], [7.75 + 1.0, 0.25, 0.25]])
+    assert float(vox.forward_types(far, None, np.array([0, 1]), 1.0).abs().max()) == 0.0
+    # surplus output channels stay zero and the same object is returned (in-place contract)
+    grid = vox.get_empty_grid(6)
+    grid.fill_(7.0)
+    res = vox.forward_types(np.array([[0.1, 0.2, 0.3]]), None, np.array([2]), 1.0, out_grid=grid)
+    assert res is grid and float(grid[3:].abs().max()) == 0.0 and float(grid[2].max()) > 0.5
+    # ragged batch with empty molecules
+    offs = np.array([0, 0, 3, 3, 5], dtype=np.int32)
+    coords = np.random.default_rng(0).uniform(-5, 5, size=(5, 3))
+    out = vox.forward_types_batch(coords, offs, None, np.array([0, 1, 2, 0, 1]), 1.0, 3)
+    assert float(out[0].abs().max()) == 0.0 and float(out[2].abs().max()) == 0.0 and float(out[1].max()) > 0
+    ref = oracle_forward_batch(0.5, 32, "scalar", "gaussian", 0.5, 8, "types", offs, coords, None,
+                               np.array([0, 1, 2, 0, 1]), None, 3, 1.0)
+    _compare(out.cpu().numpy(), ref, False)
+    # device-side validation: a type >= num_channels is flagged
+    with pytest.raises(ValueError):
+        vox.forward_types_batch(coords, offs, None, np.array([0, 1, 9, 0, 1]), 1.0, 3)
+
+
+def test_random_transform_runs_and_preserves_mass():
+    rng = np.random.default_rng(1)
+    offs, coords, types = ligand_batch(rng, 8, 4)
+    vox = mv.create_voxelizer(0.5, 64, "scalar", "binary", library="b200", blockdim=64)
+    base = vox.forward_types_batch(coords, offs, None, types, 1.0, 4)
+    np.random.seed(0)
+    aug = vox.forward_types_batch(coords, offs, None, types, 1.0, 4, random_translation=0.5, random_rotation=True)
+    assert not torch.equal(base, aug)
+    # rigid motion keeps every atom inside the 32 A box, so per-channel atom mass changes by < 20 %
+    r = (aug.sum(dim=(2, 3, 4)) + 1) / (base.sum(dim=(2, 3, 4)) + 1)
+    assert float(r.min()) > 0.8 and float(r.max()) < 1.25
