@@ -4,6 +4,7 @@
 // that would launch work fails with MVX_ERR_CUDA.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -155,16 +156,51 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     return MVX_OK;
 }
 
+// kernel selection: "cells" (warp-cell form, D % 4 == 0) is the main path; "rows" is the generic form
+// (any D, scalar stores).  MVX_KERNEL=rows|cells and MVX_LPR=2|4|16 override for experiments.
+struct KernelChoice { bool cells; int lpr; };
+
+KernelChoice choose_kernel(int nv) {
+    KernelChoice k{nv == 4, 4};
+    if (const char* e = std::getenv("MVX_KERNEL")) {
+        if (std::strcmp(e, "rows") == 0) k.cells = false;
+    }
+    if (const char* e = std::getenv("MVX_LPR")) {
+        int v = std::atoi(e);
+        if (v == 2 || v == 4 || v == 16) k.lpr = v;
+    }
+    return k;
+}
+
+template <int MODE, int CH, bool BINARY, int LPR>
+cudaError_t launch_cells(const mvx::VoxParams& vp, unsigned grid, cudaStream_t st) {
+    constexpr size_t smem = mvx::cells_smem_bytes<MODE, CH>();
+    static bool configured = false;   // per instantiation; benign race (idempotent attribute)
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, LPR>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, LPR><<<grid, mvx::kThreads, smem, st>>>(vp);
+    return cudaGetLastError();
+}
+
 template <int MODE, int CH, bool BINARY>
-cudaError_t launch_vox_nv(const mvx::VoxParams& vp, int nv, unsigned grid, cudaStream_t st) {
+cudaError_t launch_vox_nv(const mvx::VoxParams& vp, int nv, KernelChoice kc, unsigned grid, cudaStream_t st) {
+    if (kc.cells && nv == 4) {
+        if (kc.lpr == 4) return launch_cells<MODE, CH, BINARY, 4>(vp, grid, st);
+        if (kc.lpr == 16) return launch_cells<MODE, CH, BINARY, 16>(vp, grid, st);
+        return launch_cells<MODE, CH, BINARY, 2>(vp, grid, st);  // MVX_LPR=2
+    }
     if (nv == 4) mvx::mvx_voxelize_kernel<MODE, CH, BINARY, 4><<<grid, mvx::kThreads, 0, st>>>(vp);
     else mvx::mvx_voxelize_kernel<MODE, CH, BINARY, 1><<<grid, mvx::kThreads, 0, st>>>(vp);
     return cudaGetLastError();
 }
 
 template <int MODE, int CH>
-cudaError_t launch_vox_density(const mvx::VoxParams& vp, bool binary, int nv, unsigned grid, cudaStream_t st) {
-    return binary ? launch_vox_nv<MODE, CH, true>(vp, nv, grid, st) : launch_vox_nv<MODE, CH, false>(vp, nv, grid, st);
+cudaError_t launch_vox_density(const mvx::VoxParams& vp, bool binary, int nv, KernelChoice kc, unsigned grid, cudaStream_t st) {
+    return binary ? launch_vox_nv<MODE, CH, true>(vp, nv, kc, grid, st) : launch_vox_nv<MODE, CH, false>(vp, nv, kc, grid, st);
 }
 
 int pick_chunk(int mode, int nchan) {
@@ -176,20 +212,21 @@ int pick_chunk(int mode, int nchan) {
 }
 
 cudaError_t launch_vox(int mode, int ch, const mvx::VoxParams& vp, bool binary, int nv, unsigned grid, cudaStream_t st) {
-    if (mode == MVX_MODE_SINGLE) return launch_vox_density<0, 1>(vp, binary, nv, grid, st);
+    const KernelChoice kc = choose_kernel(nv);
+    if (mode == MVX_MODE_SINGLE) return launch_vox_density<0, 1>(vp, binary, nv, kc, grid, st);
     if (mode == MVX_MODE_TYPES) {
         switch (ch) {
-            case 1: return launch_vox_density<1, 1>(vp, binary, nv, grid, st);
-            case 4: return launch_vox_density<1, 4>(vp, binary, nv, grid, st);
-            case 8: return launch_vox_density<1, 8>(vp, binary, nv, grid, st);
-            default: return launch_vox_density<1, 16>(vp, binary, nv, grid, st);
+            case 1: return launch_vox_density<1, 1>(vp, binary, nv, kc, grid, st);
+            case 4: return launch_vox_density<1, 4>(vp, binary, nv, kc, grid, st);
+            case 8: return launch_vox_density<1, 8>(vp, binary, nv, kc, grid, st);
+            default: return launch_vox_density<1, 16>(vp, binary, nv, kc, grid, st);
         }
     }
     switch (ch) {
-        case 1: return launch_vox_density<2, 1>(vp, binary, nv, grid, st);
-        case 4: return launch_vox_density<2, 4>(vp, binary, nv, grid, st);
-        case 8: return launch_vox_density<2, 8>(vp, binary, nv, grid, st);
-        default: return launch_vox_density<2, 16>(vp, binary, nv, grid, st);
+        case 1: return launch_vox_density<2, 1>(vp, binary, nv, kc, grid, st);
+        case 4: return launch_vox_density<2, 4>(vp, binary, nv, kc, grid, st);
+        case 8: return launch_vox_density<2, 8>(vp, binary, nv, kc, grid, st);
+        default: return launch_vox_density<2, 16>(vp, binary, nv, kc, grid, st);
     }
 }
 

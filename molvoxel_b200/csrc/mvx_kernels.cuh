@@ -422,4 +422,267 @@ __global__ void __launch_bounds__(kThreads) mvx_voxelize_kernel(const VoxParams 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// voxelize, "warp-cell" form (the main path; needs D % 4 == 0).  Same CTA tile as above, but each
+// warp owns a compact cell of RX x RY x (4*LPR) voxels (LPR lanes along z per row), so that
+//   1. the column's staged atoms are filtered per warp with an exact sphere/box test (32 candidates per
+//      ballot) into a short warp-private list held in shared memory,
+//   2. every lane tests only that short list for its 4 voxels and records candidate hits in a bitmask,
+//   3. each lane then walks ITS OWN set bits in ascending order (= the reference's atom order), so the
+//      channel accumulation runs max-hits-per-lane times per warp instead of once per atom that touches
+//      any lane — this removes the SIMT divergence that bounded the dense (protein) workloads.
+// Zero fill of empty columns is division-free: one address computation per thread item.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStageCap = 512;   // candidates staged per round
+constexpr int kWarpList = 64;    // warp-private list capacity (64-bit hit mask)
+
+template <int CH>
+__host__ __device__ constexpr int feat_stride() { return CH + 4; }   // +4 words: conflict-free lane-private LDS.128
+
+template <int MODE, int CH>
+constexpr size_t cells_smem_bytes() {
+    return (size_t)kStageCap * (2 * sizeof(float4) + sizeof(int)) + 8 * kWarpList * (2 * sizeof(float4) + sizeof(uint16_t)) +
+           (MODE == 2 ? (size_t)kStageCap * feat_stride<CH>() * sizeof(float) : 0);
+}
+
+template <int MODE, int CH, bool BINARY, int LPR>
+__global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_cells_kernel(const VoxParams P) {
+    constexpr int ROWS = 32 / LPR;
+    constexpr int RY = (LPR == 16) ? 2 : (LPR == 8 ? 2 : 4);
+    constexpr int RX = ROWS / RY;
+    constexpr int CZ = 4 * LPR;
+    constexpr int NCX = kTile / RX, NCY = kTile / RY;
+    constexpr int FS = feat_stride<CH>();
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* sA = reinterpret_cast<float4*>(smem_raw);
+    float4* sB = sA + kStageCap;
+    int* sN = reinterpret_cast<int*>(sB + kStageCap);
+    float4* wA_all = reinterpret_cast<float4*>(sN + kStageCap);
+    float4* wB_all = wA_all + 8 * kWarpList;
+    uint16_t* wI_all = reinterpret_cast<uint16_t*>(wB_all + 8 * kWarpList);
+    float* sF = reinterpret_cast<float*>(wI_all + 8 * kWarpList);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int t = blockIdx.x;
+    const int zc = t % P.nzc; t /= P.nzc;
+    const int col = t % P.ncol;
+    const int mol = t / P.ncol;
+    const int x0 = (col / P.ncx) * kTile, y0 = (col % P.ncx) * kTile, z0 = zc * P.tz;
+    const int D = P.dim;
+    const int z1 = min(D, z0 + P.tz);
+    const size_t plane = (size_t)D * D * D;
+    float* out_mol = P.out + (size_t)mol * P.Cout * plane;
+
+    const uint2 bin = P.bins[(size_t)mol * P.ncol + col];
+    const int cnt = (int)bin.y;
+
+    if (cnt == 0) {   // empty column: pure zero fill, one address computation per thread item
+        const int lz = (z1 - z0) >> 2;
+        const int nitems = kTile * kTile * lz;
+        const int qstep = kThreads / lz, rstep = kThreads - qstep * lz;
+        int row = tid / lz, lzi = tid - row * lz;
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int item = tid; item < nitems; item += kThreads) {
+            const int x = x0 + (row >> 3), y = y0 + (row & 7);
+            if (x < D && y < D) {
+                float* p = out_mol + (size_t)P.c_begin * plane + ((size_t)x * D + y) * D + z0 + lzi * 4;
+                for (int ch = P.c_begin; ch < P.c_end; ++ch, p += plane) __stcs(reinterpret_cast<float4*>(p), zero);
+            }
+            row += qstep; lzi += rstep;
+            if (lzi >= lz) { lzi -= lz; ++row; }
+        }
+        return;
+    }
+
+    const uint32_t* list = P.lists + (size_t)P.mol_offsets[mol] * (size_t)P.maxcols + bin.x;
+    const double ox0 = (double)x0 * P.res - P.half_width;
+    const double oy0 = (double)y0 * P.res - P.half_width;
+    const double oz0 = (double)z0 * P.res - P.half_width;
+    const float resf = (float)P.res;
+    const bool single_round = cnt <= kStageCap;
+    int staged_c0 = -1;
+
+    float4* wA = wA_all + warp * kWarpList;
+    float4* wB = wB_all + warp * kWarpList;
+    uint16_t* wI = wI_all + warp * kWarpList;
+
+    const int row = lane / LPR, zq = lane % LPR;
+    const int rx = row / RY, ry = row % RY;
+    const int ncz = (z1 - z0 + CZ - 1) / CZ;
+    const int ncells = NCX * NCY * ncz;
+
+    for (int c0 = P.c_begin; c0 < P.c_end; c0 += CH) {
+        for (int cell0 = 0; cell0 < ncells; cell0 += 8) {
+            const int cell = cell0 + warp;
+            const bool cell_ok = cell < ncells;
+            const int cz = cell / (NCX * NCY), cxy = cell % (NCX * NCY);
+            const int cxl = cxy / NCY, cyl = cxy % NCY;
+            const int lx = cxl * RX + rx, ly = cyl * RY + ry, lzv = cz * CZ + zq * 4;   // tile-relative voxel
+            const int x = x0 + lx, y = y0 + ly, z = z0 + lzv;
+            const bool valid = cell_ok && x < D && y < D && z < z1;
+            const float ox = (float)((double)lx * P.res), oy = (float)((double)ly * P.res);
+            float oz[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) oz[k] = (float)((double)(lzv + k) * P.res);
+            // cell box (voxel centres) for the warp filter, tile-relative
+            const int czn = min(CZ, z1 - z0 - cz * CZ);
+            const float bhx = 0.5f * (RX - 1) * resf, bhy = 0.5f * (RY - 1) * resf, bhz = 0.5f * (czn - 1) * resf;
+            const float bcx = (cxl * RX) * resf + bhx, bcy = (cyl * RY) * resf + bhy, bcz = (cz * CZ) * resf + bhz;
+            const float slack = 1e-4f * (1.f + bcx + bcy + bcz);   // fp32 rounding of the box itself
+
+            float acc[CH][4];
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[c][k] = 0.f;
+
+            for (int r0 = 0; r0 < cnt; r0 += kStageCap) {
+                const int nc = min(kStageCap, cnt - r0);
+                if (!(single_round && staged_c0 == c0)) {
+                    __syncthreads();
+                    for (int i = tid; i < nc; i += kThreads) {
+                        const int n = (int)list[r0 + i];
+                        const AtomRec rec = P.recs[n];
+                        float r = rec.r;
+                        if (MODE == 2 && P.chan_radii != nullptr) r = P.chan_radii[c0];
+                        const float r2 = r * r;
+                        const float tau = r * P.tau_lin + r2 * P.tau_quad;
+                        float r2hi = r2 + tau;
+                        if (rec.zhi < z0 || rec.zlo >= z1) r2hi = -1.f;
+                        const int fx = rec.fx - x0, fy = rec.fy - y0, fz = rec.fz - z0;
+                        const uint32_t forb = (uint32_t)((rec.fx >= 0 && fx >= 0 && fx < kTile) ? fx : 0xFF) |
+                                              ((uint32_t)((rec.fy >= 0 && fy >= 0 && fy < kTile) ? fy : 0xFF) << 8) |
+                                              ((uint32_t)((rec.fz >= 0 && fz >= 0 && fz < 0xFFFF) ? fz : 0xFFFF) << 16);
+                        const double rs = (double)r * P.sigma;
+                        const float kc = (float)(-0.5 * 1.4426950408889634 / (rs * rs));
+                        sA[i] = make_float4((float)(rec.px - ox0), (float)(rec.py - oy0), (float)(rec.pz - oz0), r2hi);
+                        sB[i] = make_float4(r2 - tau, kc, __uint_as_float(forb), MODE == 1 ? __int_as_float(P.types[n]) : r);
+                        sN[i] = n;
+                    }
+                    if (MODE == 2) {
+                        for (int i = tid; i < nc * CH; i += kThreads) {
+                            const int j = i / CH, c = i - j * CH;
+                            const int n = (int)list[r0 + j];
+                            sF[j * FS + c] = (c0 + c < P.C) ? P.features[(size_t)n * P.C + c0 + c] : 0.f;
+                        }
+                    }
+                    __syncthreads();
+                    staged_c0 = c0;
+                }
+                if (!cell_ok) continue;   // warp-uniform
+
+                int base = 0;
+                while (base < nc) {
+                    // 1. warp filter: exact sphere / cell-box test, 32 staged atoms per ballot
+                    int wn = 0;
+                    while (base < nc && wn <= kWarpList - 32) {
+                        const int i = base + lane;
+                        bool in = false;
+                        float4 A = make_float4(0.f, 0.f, 0.f, -1.f);
+                        if (i < nc) {
+                            A = sA[i];
+                            const float ex = fmaxf(fabsf(A.x - bcx) - bhx, 0.f);
+                            const float ey = fmaxf(fabsf(A.y - bcy) - bhy, 0.f);
+                            const float ez = fmaxf(fabsf(A.z - bcz) - bhz, 0.f);
+                            in = ex * ex + ey * ey + ez * ez <= A.w + slack && A.w >= 0.f;
+                        }
+                        const uint32_t m = __ballot_sync(0xffffffffu, in);
+                        if (in) {
+                            const int pos = wn + __popc(m & ((1u << lane) - 1u));
+                            wA[pos] = A; wB[pos] = sB[i]; wI[pos] = (uint16_t)i;
+                        }
+                        wn += __popc(m);
+                        base += 32;
+                    }
+                    __syncwarp();
+                    // 2. every lane tests the warp list for its 4 voxels; candidate hits -> bitmask
+                    unsigned long long mask = 0ull;
+                    if (valid) {
+                        for (int j = 0; j < wn; ++j) {
+                            const float4 A = wA[j];
+                            const float dx = A.x - ox, dy = A.y - oy;
+                            const float dxy = dx * dx + dy * dy;
+                            float smin = 3.0e38f;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float dz = A.z - oz[k];
+                                smin = fminf(smin, dxy + dz * dz);
+                            }
+                            if (smin <= A.w) mask |= 1ull << j;
+                        }
+                    }
+                    // 3. lane-private walk over the set bits, ascending (fixed fp32 summation order)
+                    while (__any_sync(0xffffffffu, mask != 0ull)) {
+                        if (mask != 0ull) {
+                            const int j = __ffsll((long long)mask) - 1;
+                            mask &= mask - 1ull;
+                            const float4 A = wA[j];
+                            const float4 Bv = wB[j];
+                            const uint32_t forb = __float_as_uint(Bv.z);
+                            if (!((int)(forb & 0xFF) == lx || (int)((forb >> 8) & 0xFF) == ly)) {
+                                const int fz = (int)(forb >> 16);
+                                const float dx = A.x - ox, dy = A.y - oy;
+                                const float dxy = dx * dx + dy * dy;
+                                float w[4];
+                                bool any = false;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const float dz = A.z - oz[k];
+                                    const float s = dxy + dz * dz;
+                                    bool hit = s < Bv.x;
+                                    if (!hit && s <= A.w) {
+                                        const int n = sN[wI[j]];
+                                        const float r32 = (MODE == 1) ? P.recs[n].r : Bv.w;
+                                        hit = exact_hit(P.recs + n, r32, x, y, z + k, P.res, P.half_width);
+                                    }
+                                    if (lzv + k == fz) hit = false;
+                                    w[k] = hit ? (BINARY ? 1.0f : exp2f(s * Bv.y)) : 0.f;
+                                    any = any || hit;
+                                }
+                                if (any) {
+                                    if (MODE == 0) {
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) acc[0][k] += w[k];
+                                    } else if (MODE == 1) {
+                                        const int ct = __float_as_int(Bv.w) - c0;
+#pragma unroll
+                                        for (int c = 0; c < CH; ++c)
+#pragma unroll
+                                            for (int k = 0; k < 4; ++k) acc[c][k] += (ct == c) ? w[k] : 0.f;
+                                    } else {
+                                        const float* frow = sF + (int)wI[j] * FS;
+#pragma unroll
+                                        for (int c4 = 0; c4 < CH; c4 += 4) {
+                                            float f[4];
+                                            if (CH >= 4) {
+                                                const float4 fv = *reinterpret_cast<const float4*>(frow + c4);
+                                                f[0] = fv.x; f[1] = fv.y; f[2] = fv.z; f[3] = fv.w;
+                                            } else {
+                                                f[0] = frow[0]; f[1] = f[2] = f[3] = 0.f;
+                                            }
+#pragma unroll
+                                            for (int cc = 0; cc < 4 && c4 + cc < CH; ++cc)
+#pragma unroll
+                                                for (int k = 0; k < 4; ++k) acc[c4 + cc][k] = fmaf(f[cc], w[k], acc[c4 + cc][k]);
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            if (valid) {
+                float* p = out_mol + (size_t)c0 * plane + ((size_t)x * D + y) * D + z;
+#pragma unroll
+                for (int c = 0; c < CH; ++c, p += plane)
+                    if (c0 + c < P.c_end) store_vox(p, acc[c]);
+            }
+        }
+    }
+}
+
 }  // namespace mvx
