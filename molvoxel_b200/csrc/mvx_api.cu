@@ -203,6 +203,16 @@ cudaError_t launch_vox_density(const mvx::VoxParams& vp, bool binary, int nv, Ke
     return binary ? launch_vox_nv<MODE, CH, true>(vp, nv, kc, grid, st) : launch_vox_nv<MODE, CH, false>(vp, nv, kc, grid, st);
 }
 
+// column groups per molecule for the bin pass: 1 (fused kernel) once the batch alone gives two waves of
+// CTAs on the 148 SMs, otherwise enough groups to get there (at least 8 columns = one per warp each).
+int bin_groups(int B, int ncol) {
+    if (B >= 296) return 1;
+    int g = (296 + B - 1) / (B > 0 ? B : 1);
+    int gmax = (ncol + 7) / 8;
+    if (g > gmax) g = gmax;
+    return g < 1 ? 1 : g;
+}
+
 int pick_chunk(int mode, int nchan) {
     if (mode == MVX_MODE_SINGLE) return 1;
     if (nchan <= 1) return 1;
@@ -254,7 +264,8 @@ int mvx_launches_per_call(const mvx_grid_spec* spec, const mvx_batch* batch) {
     if (batch->num_mols == 0) return 0;
     const bool chan_feat = batch->mode == MVX_MODE_FEATURES && spec->radii_type == MVX_RADII_CHANNEL_WISE;
     int nvox = chan_feat ? batch->num_channels : 1;
-    return (batch->total_atoms > 0 ? 1 : 0) + 1 + nvox;   // prep + bin + voxelize
+    const int nbin = bin_groups(batch->num_mols, pl.ncol) <= 1 ? 1 : 2;
+    return (batch->total_atoms > 0 ? 1 : 0) + nbin + nvox;   // prep + bin + voxelize
 }
 
 int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, void* workspace,
@@ -299,9 +310,15 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, 
         mvx::BinParams bp;
         bp.B = B; bp.ncol = pl.ncol; bp.ncx = pl.geo.ncx; bp.maxcols = pl.maxcols;
         bp.mol_offsets = batch->mol_offsets; bp.colrange = colrange; bp.bins = bins; bp.lists = lists;
-        const int threads = (N / (B > 0 ? B : 1) > 512) ? 1024 : 256;
         const size_t smem = 2 * (size_t)pl.ncol * sizeof(uint32_t);
-        mvx::mvx_bin_kernel<<<(unsigned)B, threads, smem, st>>>(bp);
+        const int groups = bin_groups(B, pl.ncol);
+        if (groups <= 1) {
+            mvx::mvx_bin_kernel<<<(unsigned)B, 256, smem, st>>>(bp);
+        } else {   // few large molecules: spread each molecule's columns over several CTAs
+            mvx::mvx_bin_count_kernel<<<(unsigned)(B * groups), 256, 0, st>>>(bp, groups);
+            MVX_CUDA_OK(cudaGetLastError());
+            mvx::mvx_bin_fill_kernel<<<(unsigned)(B * groups), 256, smem, st>>>(bp, groups);
+        }
         MVX_CUDA_OK(cudaGetLastError());
     }
     prof_mark(st, 2);

@@ -196,6 +196,47 @@ __device__ __forceinline__ bool col_overlaps(uint32_t cr, int cx, int cy) {
     return cx >= cx0 && cx <= cx1 && cy >= cy0 && cy <= cy1;
 }
 
+// Counts (and, when `seg` is given, fills) one column's list.  128 atoms per iteration: four
+// independent loads in flight per lane, ballots keep ascending atom order.
+__device__ __forceinline__ uint32_t bin_scan_column(const uint32_t* __restrict__ cr, int V, int cx, int cy, int lane,
+                                                    uint32_t* seg, uint32_t pos, int a0) {
+    uint32_t cnt = 0;
+    for (int base = 0; base < V; base += 128) {
+        uint32_t c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * 32 + lane;
+            c[u] = i < V ? __ldg(cr + i) : 0x000000FFu;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool in = col_overlaps(c[u], cx, cy);
+            const uint32_t m = __ballot_sync(0xffffffffu, in);
+            if (seg != nullptr && in) seg[pos + cnt + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(a0 + base + u * 32 + lane);
+            cnt += __popc(m);
+        }
+    }
+    return cnt;
+}
+
+// exclusive scan of s_cnt[0..n) into s_off[0..n) by warp 0
+__device__ __forceinline__ void bin_scan_counts(const uint32_t* s_cnt, uint32_t* s_off, int n, int lane) {
+    uint32_t carry = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const uint32_t v = i < n ? s_cnt[i] : 0;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (i < n) s_off[i] = carry + x - v;
+        carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+}
+
+// Fused form (many molecules): one CTA per molecule does count, scan and fill.
 __global__ void mvx_bin_kernel(const BinParams P) {
     extern __shared__ uint32_t s_u32[];
     uint32_t* s_cnt = s_u32;            // [ncol]
@@ -204,46 +245,50 @@ __global__ void mvx_bin_kernel(const BinParams P) {
     const int a0 = P.mol_offsets[mol], V = P.mol_offsets[mol + 1] - a0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t* cr = P.colrange + a0;
-    const int vpad = (V + 31) & ~31;
 
     for (int col = warp; col < P.ncol; col += nwarps) {
-        const int cx = col / P.ncx, cy = col % P.ncx;
-        uint32_t cnt = 0;
-        for (int i = lane; i < vpad; i += 32) {
-            bool in = (i < V) && col_overlaps(cr[i], cx, cy);
-            cnt += __popc(__ballot_sync(0xffffffffu, in));
-        }
+        const uint32_t cnt = bin_scan_column(cr, V, col / P.ncx, col % P.ncx, lane, nullptr, 0, a0);
         if (lane == 0) s_cnt[col] = cnt;
     }
     __syncthreads();
-    if (warp == 0) {   // exclusive scan over the columns, 32 at a time
-        uint32_t carry = 0;
-        for (int base = 0; base < P.ncol; base += 32) {
-            int i = base + lane;
-            uint32_t v = i < P.ncol ? s_cnt[i] : 0, x = v;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-                if (lane >= d) x += y;
-            }
-            if (i < P.ncol) s_off[i] = carry + x - v;
-            carry += __shfl_sync(0xffffffffu, x, 31);
-        }
-    }
+    if (warp == 0) bin_scan_counts(s_cnt, s_off, P.ncol, lane);
     __syncthreads();
     uint32_t* seg = P.lists + (size_t)a0 * (size_t)P.maxcols;
     for (int col = warp; col < P.ncol; col += nwarps) {
-        const int cx = col / P.ncx, cy = col % P.ncx;
-        uint32_t pos = s_off[col];
-        if (s_cnt[col] != 0) {
-            for (int i = lane; i < vpad; i += 32) {
-                bool in = (i < V) && col_overlaps(cr[i], cx, cy);
-                uint32_t m = __ballot_sync(0xffffffffu, in);
-                if (in) seg[pos + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(a0 + i);
-                pos += __popc(m);
-            }
-        }
+        if (s_cnt[col] != 0) bin_scan_column(cr, V, col / P.ncx, col % P.ncx, lane, seg, s_off[col], a0);
         if (lane == 0) P.bins[(size_t)mol * P.ncol + col] = make_uint2(s_off[col], s_cnt[col]);
+    }
+}
+
+// Split form (few, large molecules): grid = (molecule, column group) so that small batches still fill
+// the 148 SMs.  Pass 1 counts into bins[].y; pass 2 rescans the molecule's counts and fills its group.
+__global__ void mvx_bin_count_kernel(const BinParams P, int groups) {
+    const int mol = blockIdx.x / groups, grp = blockIdx.x % groups;
+    const int a0 = P.mol_offsets[mol], V = P.mol_offsets[mol + 1] - a0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t* cr = P.colrange + a0;
+    for (int col = grp * nwarps + warp; col < P.ncol; col += groups * nwarps) {
+        const uint32_t cnt = bin_scan_column(cr, V, col / P.ncx, col % P.ncx, lane, nullptr, 0, a0);
+        if (lane == 0) P.bins[(size_t)mol * P.ncol + col].y = cnt;
+    }
+}
+
+__global__ void mvx_bin_fill_kernel(const BinParams P, int groups) {
+    extern __shared__ uint32_t s_u32[];
+    uint32_t* s_cnt = s_u32;
+    uint32_t* s_off = s_u32 + P.ncol;
+    const int mol = blockIdx.x / groups, grp = blockIdx.x % groups;
+    const int a0 = P.mol_offsets[mol], V = P.mol_offsets[mol + 1] - a0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t* cr = P.colrange + a0;
+    for (int col = threadIdx.x; col < P.ncol; col += blockDim.x) s_cnt[col] = P.bins[(size_t)mol * P.ncol + col].y;
+    __syncthreads();
+    if (warp == 0) bin_scan_counts(s_cnt, s_off, P.ncol, lane);
+    __syncthreads();
+    uint32_t* seg = P.lists + (size_t)a0 * (size_t)P.maxcols;
+    for (int col = grp * nwarps + warp; col < P.ncol; col += groups * nwarps) {
+        if (s_cnt[col] != 0) bin_scan_column(cr, V, col / P.ncx, col % P.ncx, lane, seg, s_off[col], a0);
+        if (lane == 0) P.bins[(size_t)mol * P.ncol + col].x = s_off[col];
     }
 }
 
@@ -266,6 +311,13 @@ __device__ __noinline__ bool exact_hit(const AtomRec* __restrict__ rec, float r3
     double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
     float d32 = __double2float_rn(__dsqrt_rn(s));
     return __fdiv_rn(d32, r32) <= 1.0f;
+}
+
+// 2^x for x <= 0 by the SFU (ex2.approx: max rel. error 2^-22, inside the 1e-5 parity tolerance)
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 __device__ __forceinline__ void store_vox(float* p, const float (&v)[4]) {
@@ -597,76 +649,88 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_cells_kernel(const V
                         base += 32;
                     }
                     __syncwarp();
-                    // 2. every lane tests the warp list for its 4 voxels; candidate hits -> bitmask
-                    unsigned long long mask = 0ull;
+                    // 2. every lane tests the warp list for its 4 voxels (nearest of the 4 along z); candidate
+                    //    hits -> two 32-bit masks.  The decision proper (incl. the exact band) is taken in 3.
+                    uint32_t mask_lo = 0u, mask_hi = 0u;
                     if (valid) {
-                        for (int j = 0; j < wn; ++j) {
+                        const int n_lo = min(wn, 32);
+                        for (int j = 0; j < n_lo; ++j) {
                             const float4 A = wA[j];
                             const float dx = A.x - ox, dy = A.y - oy;
-                            const float dxy = dx * dx + dy * dy;
-                            float smin = 3.0e38f;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const float dz = A.z - oz[k];
-                                smin = fminf(smin, dxy + dz * dz);
-                            }
-                            if (smin <= A.w) mask |= 1ull << j;
+                            const float dzc = A.z - fminf(fmaxf(A.z, oz[0]), oz[3]);
+                            const float smin = fmaf(dzc, dzc, fmaf(dx, dx, dy * dy));
+                            if (smin <= A.w) mask_lo |= 1u << j;
+                        }
+                        for (int j = 32; j < wn; ++j) {
+                            const float4 A = wA[j];
+                            const float dx = A.x - ox, dy = A.y - oy;
+                            const float dzc = A.z - fminf(fmaxf(A.z, oz[0]), oz[3]);
+                            const float smin = fmaf(dzc, dzc, fmaf(dx, dx, dy * dy));
+                            if (smin <= A.w) mask_hi |= 1u << (j - 32);
                         }
                     }
                     // 3. lane-private walk over the set bits, ascending (fixed fp32 summation order)
-                    while (__any_sync(0xffffffffu, mask != 0ull)) {
-                        if (mask != 0ull) {
-                            const int j = __ffsll((long long)mask) - 1;
-                            mask &= mask - 1ull;
+                    while (__any_sync(0xffffffffu, (mask_lo | mask_hi) != 0u)) {
+                        if ((mask_lo | mask_hi) != 0u) {
+                            int j;
+                            if (mask_lo != 0u) { j = __ffs((int)mask_lo) - 1; mask_lo &= mask_lo - 1u; }
+                            else { j = 31 + __ffs((int)mask_hi); mask_hi &= mask_hi - 1u; }
                             const float4 A = wA[j];
                             const float4 Bv = wB[j];
+                            const float dx = A.x - ox, dy = A.y - oy;
+                            const float dxy = fmaf(dx, dx, dy * dy);
+                            float sk[4];
+                            bool hit[4];
+                            bool band = false;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float dz = A.z - oz[k];
+                                sk[k] = fmaf(dz, dz, dxy);
+                                hit[k] = sk[k] < Bv.x;
+                                band = band || (!hit[k] && sk[k] <= A.w);
+                            }
+                            if (band) {   // rare: replay the reference's fp64 arithmetic for the voxels inside the band
+                                const int n = sN[wI[j]];
+                                const float r32 = (MODE == 1) ? P.recs[n].r : Bv.w;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (!hit[k] && sk[k] <= A.w) hit[k] = exact_hit(P.recs + n, r32, x, y, z + k, P.res, P.half_width);
+                            }
                             const uint32_t forb = __float_as_uint(Bv.z);
-                            if (!((int)(forb & 0xFF) == lx || (int)((forb >> 8) & 0xFF) == ly)) {
-                                const int fz = (int)(forb >> 16);
-                                const float dx = A.x - ox, dy = A.y - oy;
-                                const float dxy = dx * dx + dy * dy;
+                            if (forb != 0xFFFFFFFFu) {   // block-cull emulation: planes this atom must not touch
+                                const bool row_off = (int)(forb & 0xFF) == lx || (int)((forb >> 8) & 0xFF) == ly;
+                                const int fz = (int)(forb >> 16) - lzv;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) hit[k] = hit[k] && !row_off && fz != k;
+                            }
+                            if (hit[0] || hit[1] || hit[2] || hit[3]) {
                                 float w[4];
-                                bool any = false;
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    const float dz = A.z - oz[k];
-                                    const float s = dxy + dz * dz;
-                                    bool hit = s < Bv.x;
-                                    if (!hit && s <= A.w) {
-                                        const int n = sN[wI[j]];
-                                        const float r32 = (MODE == 1) ? P.recs[n].r : Bv.w;
-                                        hit = exact_hit(P.recs + n, r32, x, y, z + k, P.res, P.half_width);
-                                    }
-                                    if (lzv + k == fz) hit = false;
-                                    w[k] = hit ? (BINARY ? 1.0f : exp2f(s * Bv.y)) : 0.f;
-                                    any = any || hit;
-                                }
-                                if (any) {
-                                    if (MODE == 0) {
+                                for (int k = 0; k < 4; ++k) w[k] = hit[k] ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
+                                if (MODE == 0) {
 #pragma unroll
-                                        for (int k = 0; k < 4; ++k) acc[0][k] += w[k];
-                                    } else if (MODE == 1) {
-                                        const int ct = __float_as_int(Bv.w) - c0;
+                                    for (int k = 0; k < 4; ++k) acc[0][k] += w[k];
+                                } else if (MODE == 1) {
+                                    const int ct = __float_as_int(Bv.w) - c0;
 #pragma unroll
-                                        for (int c = 0; c < CH; ++c)
+                                    for (int c = 0; c < CH; ++c)
 #pragma unroll
-                                            for (int k = 0; k < 4; ++k) acc[c][k] += (ct == c) ? w[k] : 0.f;
-                                    } else {
-                                        const float* frow = sF + (int)wI[j] * FS;
+                                        for (int k = 0; k < 4; ++k) acc[c][k] += (ct == c) ? w[k] : 0.f;
+                                } else {
+                                    const float* frow = sF + (int)wI[j] * FS;
 #pragma unroll
-                                        for (int c4 = 0; c4 < CH; c4 += 4) {
-                                            float f[4];
-                                            if (CH >= 4) {
-                                                const float4 fv = *reinterpret_cast<const float4*>(frow + c4);
-                                                f[0] = fv.x; f[1] = fv.y; f[2] = fv.z; f[3] = fv.w;
-                                            } else {
-                                                f[0] = frow[0]; f[1] = f[2] = f[3] = 0.f;
-                                            }
-#pragma unroll
-                                            for (int cc = 0; cc < 4 && c4 + cc < CH; ++cc)
-#pragma unroll
-                                                for (int k = 0; k < 4; ++k) acc[c4 + cc][k] = fmaf(f[cc], w[k], acc[c4 + cc][k]);
+                                    for (int c4 = 0; c4 < CH; c4 += 4) {
+                                        float f[4];
+                                        if (CH >= 4) {
+                                            const float4 fv = *reinterpret_cast<const float4*>(frow + c4);
+                                            f[0] = fv.x; f[1] = fv.y; f[2] = fv.z; f[3] = fv.w;
+                                        } else {
+                                            f[0] = frow[0]; f[1] = f[2] = f[3] = 0.f;
                                         }
+#pragma unroll
+                                        for (int cc = 0; cc < 4 && c4 + cc < CH; ++cc)
+#pragma unroll
+                                            for (int k = 0; k < 4; ++k) acc[c4 + cc][k] = fmaf(f[cc], w[k], acc[c4 + cc][k]);
                                     }
                                 }
                             }
