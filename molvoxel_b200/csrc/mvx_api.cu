@@ -327,7 +327,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, 
         vp.res = pl.geo.res; vp.half_width = pl.geo.half_width; vp.sigma = spec->sigma;
         vp.tau_lin = pl.tau_lin; vp.tau_quad = pl.tau_quad;
         vp.dim = spec->dimension; vp.ncx = pl.geo.ncx; vp.ncol = pl.ncol; vp.nzc = pl.nzc; vp.tz = pl.tz;
-        vp.C = C; vp.Cout = batch->out_channels; vp.maxcols = pl.maxcols;
+        vp.C = C; vp.Cout = batch->out_channels; vp.maxcols = pl.maxcols; vp.cull = pl.geo.nb > 1;
         vp.mol_offsets = batch->mol_offsets; vp.recs = recs; vp.bins = bins; vp.lists = lists;
         vp.types = batch->types; vp.features = batch->features; vp.chan_radii = nullptr; vp.out = out;
         const unsigned long long nblk = (unsigned long long)B * pl.ncol * pl.nzc;

@@ -73,6 +73,7 @@ struct VoxParams {
     int dim, ncx, ncol, nzc, tz;
     int C, Cout, c_begin, c_end;
     int maxcols;
+    int cull;                  // 1: the reference's block cull is emulated (compat_blockdim < dimension)
     const int32_t* mol_offsets;
     const AtomRec* recs;
     const uint2* bins;
@@ -477,44 +478,51 @@ __global__ void __launch_bounds__(kThreads) mvx_voxelize_kernel(const VoxParams 
 
 // ---------------------------------------------------------------------------------------------
 // voxelize, "warp-cell" form (the main path; needs D % 4 == 0).  Same CTA tile as above, but each
-// warp owns a compact cell of RX x RY x (4*LPR) voxels (LPR lanes along z per row), so that
-//   1. the column's staged atoms are filtered per warp with an exact sphere/box test (32 candidates per
-//      ballot) into a short warp-private list held in shared memory,
-//   2. every lane tests only that short list for its 4 voxels and records candidate hits in a bitmask,
-//   3. each lane then walks ITS OWN set bits in ascending order (= the reference's atom order), so the
+// warp owns a compact cell of RX x RY x (4*LPR) voxels (LPR lanes along z per row):
+//   0. staging (once per tile): tile-relative fp32 atom records in shared memory plus, per atom, a
+//      32-bit mask of the tile's cells whose voxel-centre box its cutoff sphere reaches (exact test),
+//   1. a warp compacts the atoms whose mask names its cell into a short warp-private list
+//      (32 staged atoms per ballot; ascending order is kept),
+//   2. every lane tests that short list for its 4 voxels and records candidate hits in a bitmask,
+//   3. each lane walks ITS OWN set bits in ascending order (= the reference's atom order), so the
 //      channel accumulation runs max-hits-per-lane times per warp instead of once per atom that touches
 //      any lane — this removes the SIMT divergence that bounded the dense (protein) workloads.
 // Zero fill of empty columns is division-free: one address computation per thread item.
 // ---------------------------------------------------------------------------------------------
 constexpr int kStageCap = 512;   // candidates staged per round
-constexpr int kWarpList = 64;    // warp-private list capacity (64-bit hit mask)
+constexpr int kWarpList = 64;    // warp-private list capacity (two 32-bit hit masks)
+constexpr uint32_t kNoForb = 0xFFFFFFFFu;
 
 template <int CH>
 __host__ __device__ constexpr int feat_stride() { return CH + 4; }   // +4 words: conflict-free lane-private LDS.128
 
 template <int MODE, int CH>
 constexpr size_t cells_smem_bytes() {
-    return (size_t)kStageCap * (2 * sizeof(float4) + sizeof(int)) + 8 * kWarpList * (2 * sizeof(float4) + sizeof(uint16_t)) +
+    return (size_t)kStageCap * (2 * sizeof(float4) + sizeof(int) + sizeof(uint32_t)) +
+           8 * kWarpList * (2 * sizeof(float4) + sizeof(uint16_t)) + 32 * sizeof(float4) +
            (MODE == 2 ? (size_t)kStageCap * feat_stride<CH>() * sizeof(float) : 0);
 }
 
 template <int MODE, int CH, bool BINARY, int LPR>
 __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_cells_kernel(const VoxParams P) {
     constexpr int ROWS = 32 / LPR;
-    constexpr int RY = (LPR == 16) ? 2 : (LPR == 8 ? 2 : 4);
+    constexpr int RY = (LPR >= 8) ? 2 : 4;
     constexpr int RX = ROWS / RY;
     constexpr int CZ = 4 * LPR;
     constexpr int NCX = kTile / RX, NCY = kTile / RY;
     constexpr int FS = feat_stride<CH>();
+    static_assert(NCX * NCY * (64 / CZ) <= 32, "cell mask is 32 bits");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* sA = reinterpret_cast<float4*>(smem_raw);
-    float4* sB = sA + kStageCap;
-    int* sN = reinterpret_cast<int*>(sB + kStageCap);
-    float4* wA_all = reinterpret_cast<float4*>(sN + kStageCap);
+    float4* sA = reinterpret_cast<float4*>(smem_raw);        // rel x, rel y, rel z, r^2 + tau
+    float4* sB = sA + kStageCap;                             // r^2 - tau, gaussian coef, forbidden planes, type | radius
+    int* sN = reinterpret_cast<int*>(sB + kStageCap);        // global atom id (exact recheck)
+    uint32_t* sM = reinterpret_cast<uint32_t*>(sN + kStageCap);   // cells reached by the cutoff sphere
+    float4* wA_all = reinterpret_cast<float4*>(sM + kStageCap);
     float4* wB_all = wA_all + 8 * kWarpList;
     uint16_t* wI_all = reinterpret_cast<uint16_t*>(wB_all + 8 * kWarpList);
-    float* sF = reinterpret_cast<float*>(wI_all + 8 * kWarpList);
+    float4* sBox = reinterpret_cast<float4*>(wI_all + 8 * kWarpList);   // per cell: box centre x, y, z, half z
+    float* sF = reinterpret_cast<float*>(sBox + 32);               // features [kStageCap][CH + 4]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int t = blockIdx.x;
@@ -564,6 +572,15 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_cells_kernel(const V
     const int rx = row / RY, ry = row % RY;
     const int ncz = (z1 - z0 + CZ - 1) / CZ;
     const int ncells = NCX * NCY * ncz;
+    // half extents of a cell's voxel-centre box (x, y constant; z shorter in the last layer)
+    const float bhx = 0.5f * (RX - 1) * resf, bhy = 0.5f * (RY - 1) * resf;
+    const float inv_res = 1.0f / resf;
+    if (tid < 32) {
+        const int bz = tid / (NCX * NCY), bxy = tid % (NCX * NCY);
+        const int czn = max(1, min(CZ, z1 - z0 - bz * CZ));
+        const float bhz = 0.5f * (czn - 1) * resf;
+        sBox[tid] = make_float4(((bxy / NCY) * RX) * resf + bhx, ((bxy % NCY) * RY) * resf + bhy, (bz * CZ) * resf + bhz, bhz);
+    }
 
     for (int c0 = P.c_begin; c0 < P.c_end; c0 += CH) {
         for (int cell0 = 0; cell0 < ncells; cell0 += 8) {
@@ -574,15 +591,11 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_cells_kernel(const V
             const int lx = cxl * RX + rx, ly = cyl * RY + ry, lzv = cz * CZ + zq * 4;   // tile-relative voxel
             const int x = x0 + lx, y = y0 + ly, z = z0 + lzv;
             const bool valid = cell_ok && x < D && y < D && z < z1;
+            const uint32_t lane_key = (uint32_t)lx | ((uint32_t)ly << 8);
             const float ox = (float)((double)lx * P.res), oy = (float)((double)ly * P.res);
             float oz[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) oz[k] = (float)((double)(lzv + k) * P.res);
-            // cell box (voxel centres) for the warp filter, tile-relative
-            const int czn = min(CZ, z1 - z0 - cz * CZ);
-            const float bhx = 0.5f * (RX - 1) * resf, bhy = 0.5f * (RY - 1) * resf, bhz = 0.5f * (czn - 1) * resf;
-            const float bcx = (cxl * RX) * resf + bhx, bcy = (cyl * RY) * resf + bhy, bcz = (cz * CZ) * resf + bhz;
-            const float slack = 1e-4f * (1.f + bcx + bcy + bcz);   // fp32 rounding of the box itself
 
             float acc[CH][4];
 #pragma unroll
@@ -601,15 +614,16 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_cells_kernel(const V
                         if (MODE == 2 && P.chan_radii != nullptr) r = P.chan_radii[c0];
                         const float r2 = r * r;
                         const float tau = r * P.tau_lin + r2 * P.tau_quad;
-                        float r2hi = r2 + tau;
-                        if (rec.zhi < z0 || rec.zlo >= z1) r2hi = -1.f;
+                        const float r2hi = r2 + tau;
                         const int fx = rec.fx - x0, fy = rec.fy - y0, fz = rec.fz - z0;
                         const uint32_t forb = (uint32_t)((rec.fx >= 0 && fx >= 0 && fx < kTile) ? fx : 0xFF) |
                                               ((uint32_t)((rec.fy >= 0 && fy >= 0 && fy < kTile) ? fy : 0xFF) << 8) |
                                               ((uint32_t)((rec.fz >= 0 && fz >= 0 && fz < 0xFFFF) ? fz : 0xFFFF) << 16);
                         const double rs = (double)r * P.sigma;
                         const float kc = (float)(-0.5 * 1.4426950408889634 / (rs * rs));
-                        sA[i] = make_float4((float)(rec.px - ox0), (float)(rec.py - oy0), (float)(rec.pz - oz0), r2hi);
+                        const float ax = (float)(rec.px - ox0), ay = (float)(rec.py - oy0), az = (float)(rec.pz - oz0);
+                        const bool z_out = rec.zhi < z0 || rec.zlo >= z1;   // outside this z chunk: reaches no cell
+                        sA[i] = make_float4(ax, ay, az, z_out ? -1.f : r2hi);
                         sB[i] = make_float4(r2 - tau, kc, __uint_as_float(forb), MODE == 1 ? __int_as_float(P.types[n]) : r);
                         sN[i] = n;
                     }
@@ -621,29 +635,36 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_cells_kernel(const V
                         }
                     }
                     __syncthreads();
+                    // cell masks: lane = cell, one staged atom per warp iteration, exact sphere / voxel-centre-box
+                    // test; the ballot IS the atom's 32-bit mask of cells its cutoff sphere reaches
+                    {
+                        const float4 box = sBox[lane];
+                        for (int i = warp; i < nc; i += kThreads / 32) {
+                            const float4 A = sA[i];
+                            const float ex = fmaxf(fabsf(A.x - box.x) - bhx, 0.f);
+                            const float ey = fmaxf(fabsf(A.y - box.y) - bhy, 0.f);
+                            const float ez = fmaxf(fabsf(A.z - box.z) - box.w, 0.f);
+                            const bool in = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) <= A.w + 1e-4f * (1.f + A.w) && lane < ncells;
+                            const uint32_t m = __ballot_sync(0xffffffffu, in);
+                            if (lane == 0) sM[i] = m;
+                        }
+                    }
+                    __syncthreads();
                     staged_c0 = c0;
                 }
                 if (!cell_ok) continue;   // warp-uniform
 
                 int base = 0;
                 while (base < nc) {
-                    // 1. warp filter: exact sphere / cell-box test, 32 staged atoms per ballot
+                    // 1. warp filter: compact the staged atoms whose cell mask names this cell
                     int wn = 0;
                     while (base < nc && wn <= kWarpList - 32) {
                         const int i = base + lane;
-                        bool in = false;
-                        float4 A = make_float4(0.f, 0.f, 0.f, -1.f);
-                        if (i < nc) {
-                            A = sA[i];
-                            const float ex = fmaxf(fabsf(A.x - bcx) - bhx, 0.f);
-                            const float ey = fmaxf(fabsf(A.y - bcy) - bhy, 0.f);
-                            const float ez = fmaxf(fabsf(A.z - bcz) - bhz, 0.f);
-                            in = ex * ex + ey * ey + ez * ez <= A.w + slack && A.w >= 0.f;
-                        }
+                        const bool in = (i < nc) && ((sM[i] >> cell) & 1u);
                         const uint32_t m = __ballot_sync(0xffffffffu, in);
                         if (in) {
                             const int pos = wn + __popc(m & ((1u << lane) - 1u));
-                            wA[pos] = A; wB[pos] = sB[i]; wI[pos] = (uint16_t)i;
+                            wA[pos] = sA[i]; wB[pos] = sB[i]; wI[pos] = (uint16_t)i;
                         }
                         wn += __popc(m);
                         base += 32;
@@ -657,14 +678,16 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_cells_kernel(const V
                         for (int j = 0; j < n_lo; ++j) {
                             const float4 A = wA[j];
                             const float dx = A.x - ox, dy = A.y - oy;
-                            const float dzc = A.z - fminf(fmaxf(A.z, oz[0]), oz[3]);
+                            const float tz_ = A.z - oz[0];
+                            const float dzc = fmaf(-resf, fminf(fmaxf(rintf(tz_ * inv_res), 0.f), 3.f), tz_);   // to the nearest of the 4
                             const float smin = fmaf(dzc, dzc, fmaf(dx, dx, dy * dy));
                             if (smin <= A.w) mask_lo |= 1u << j;
                         }
                         for (int j = 32; j < wn; ++j) {
                             const float4 A = wA[j];
                             const float dx = A.x - ox, dy = A.y - oy;
-                            const float dzc = A.z - fminf(fmaxf(A.z, oz[0]), oz[3]);
+                            const float tz_ = A.z - oz[0];
+                            const float dzc = fmaf(-resf, fminf(fmaxf(rintf(tz_ * inv_res), 0.f), 3.f), tz_);   // to the nearest of the 4
                             const float smin = fmaf(dzc, dzc, fmaf(dx, dx, dy * dy));
                             if (smin <= A.w) mask_hi |= 1u << (j - 32);
                         }
@@ -679,59 +702,59 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_cells_kernel(const V
                             const float4 Bv = wB[j];
                             const float dx = A.x - ox, dy = A.y - oy;
                             const float dxy = fmaf(dx, dx, dy * dy);
-                            float sk[4];
-                            bool hit[4];
+                            // block-cull emulation: voxels on this atom's forbidden planes take nothing from it
+                            bool off[4] = {false, false, false, false};
+                            if (P.cull) {   // uniform
+                                const uint32_t forb = __float_as_uint(Bv.z);
+                                const uint32_t tx = forb ^ lane_key;
+                                const bool row_off = (tx & 0xFFu) == 0u || (tx & 0xFF00u) == 0u;
+                                const int dzf = (int)(forb >> 16) - lzv;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) off[k] = row_off || dzf == k;
+                            }
+                            float sk[4], w[4];
                             bool band = false;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const float dz = A.z - oz[k];
                                 sk[k] = fmaf(dz, dz, dxy);
-                                hit[k] = sk[k] < Bv.x;
-                                band = band || (!hit[k] && sk[k] <= A.w);
+                                w[k] = (sk[k] < Bv.x && !off[k]) ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
+                                band = band || (sk[k] >= Bv.x && sk[k] <= A.w);
                             }
-                            if (band) {   // rare: replay the reference's fp64 arithmetic for the voxels inside the band
+                            if (band) {   // rare: voxels inside the tolerance band replay the reference's fp64 arithmetic
                                 const int n = sN[wI[j]];
                                 const float r32 = (MODE == 1) ? P.recs[n].r : Bv.w;
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    if (!hit[k] && sk[k] <= A.w) hit[k] = exact_hit(P.recs + n, r32, x, y, z + k, P.res, P.half_width);
+                                for (int k = 0; k < 4; ++k) {
+                                    if (sk[k] >= Bv.x && sk[k] <= A.w && !off[k] &&
+                                        exact_hit(P.recs + n, r32, x, y, z + k, P.res, P.half_width))
+                                        w[k] = BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y);
+                                }
                             }
-                            const uint32_t forb = __float_as_uint(Bv.z);
-                            if (forb != 0xFFFFFFFFu) {   // block-cull emulation: planes this atom must not touch
-                                const bool row_off = (int)(forb & 0xFF) == lx || (int)((forb >> 8) & 0xFF) == ly;
-                                const int fz = (int)(forb >> 16) - lzv;
+                            if (MODE == 0) {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) hit[k] = hit[k] && !row_off && fz != k;
-                            }
-                            if (hit[0] || hit[1] || hit[2] || hit[3]) {
-                                float w[4];
+                                for (int k = 0; k < 4; ++k) acc[0][k] += w[k];
+                            } else if (MODE == 1) {
+                                const int ct = __float_as_int(Bv.w) - c0;
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) w[k] = hit[k] ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
-                                if (MODE == 0) {
+                                for (int c = 0; c < CH; ++c)
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k) acc[0][k] += w[k];
-                                } else if (MODE == 1) {
-                                    const int ct = __float_as_int(Bv.w) - c0;
+                                    for (int k = 0; k < 4; ++k) acc[c][k] += (ct == c) ? w[k] : 0.f;
+                            } else {
+                                const float* frow = sF + (int)wI[j] * FS;
 #pragma unroll
-                                    for (int c = 0; c < CH; ++c)
-#pragma unroll
-                                        for (int k = 0; k < 4; ++k) acc[c][k] += (ct == c) ? w[k] : 0.f;
-                                } else {
-                                    const float* frow = sF + (int)wI[j] * FS;
-#pragma unroll
-                                    for (int c4 = 0; c4 < CH; c4 += 4) {
-                                        float f[4];
-                                        if (CH >= 4) {
-                                            const float4 fv = *reinterpret_cast<const float4*>(frow + c4);
-                                            f[0] = fv.x; f[1] = fv.y; f[2] = fv.z; f[3] = fv.w;
-                                        } else {
-                                            f[0] = frow[0]; f[1] = f[2] = f[3] = 0.f;
-                                        }
-#pragma unroll
-                                        for (int cc = 0; cc < 4 && c4 + cc < CH; ++cc)
-#pragma unroll
-                                            for (int k = 0; k < 4; ++k) acc[c4 + cc][k] = fmaf(f[cc], w[k], acc[c4 + cc][k]);
+                                for (int c4 = 0; c4 < CH; c4 += 4) {
+                                    float f[4];
+                                    if (CH >= 4) {
+                                        const float4 fv = *reinterpret_cast<const float4*>(frow + c4);
+                                        f[0] = fv.x; f[1] = fv.y; f[2] = fv.z; f[3] = fv.w;
+                                    } else {
+                                        f[0] = frow[0]; f[1] = f[2] = f[3] = 0.f;
                                     }
+#pragma unroll
+                                    for (int cc = 0; cc < 4 && c4 + cc < CH; ++cc)
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) acc[c4 + cc][k] = fmaf(f[cc], w[k], acc[c4 + cc][k]);
                                 }
                             }
                         }
@@ -741,9 +764,14 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_cells_kernel(const V
             }
             if (valid) {
                 float* p = out_mol + (size_t)c0 * plane + ((size_t)x * D + y) * D + z;
+                if (c0 + CH <= P.c_end) {
 #pragma unroll
-                for (int c = 0; c < CH; ++c, p += plane)
-                    if (c0 + c < P.c_end) store_vox(p, acc[c]);
+                    for (int c = 0; c < CH; ++c, p += plane) store_vox(p, acc[c]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CH; ++c, p += plane)
+                        if (c0 + c < P.c_end) store_vox(p, acc[c]);
+                }
             }
         }
     }
