@@ -215,6 +215,10 @@ int bin_groups(int B, int ncol) {
 
 int pick_chunk(int mode, int nchan) {
     if (mode == MVX_MODE_SINGLE) return 1;
+    if (const char* e = std::getenv("MVX_CH")) {   // experiments: force the channel chunk
+        int v = std::atoi(e);
+        if (v == 1 || v == 4 || v == 8 || v == 16) return v;
+    }
     if (nchan <= 1) return 1;
     if (nchan <= 4) return 4;
     if (nchan <= 8) return 8;

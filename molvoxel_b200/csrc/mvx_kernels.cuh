@@ -504,7 +504,7 @@ constexpr size_t cells_smem_bytes() {
 }
 
 template <int MODE, int CH, bool BINARY, int LPR>
-__global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_cells_kernel(const VoxParams P) {
+__global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cells_kernel(const VoxParams P) {
     constexpr int ROWS = 32 / LPR;
     constexpr int RY = (LPR >= 8) ? 2 : 4;
     constexpr int RX = ROWS / RY;
@@ -674,23 +674,19 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_cells_kernel(const V
                     //    hits -> two 32-bit masks.  The decision proper (incl. the exact band) is taken in 3.
                     uint32_t mask_lo = 0u, mask_hi = 0u;
                     if (valid) {
+                        auto near_hit = [&](const float4 A) -> bool {
+                            const float dx = A.x - ox, dy = A.y - oy;
+                            const float tz_ = A.z - oz[0];
+                            const float dzc = fmaf(-resf, fminf(fmaxf(rintf(tz_ * inv_res), 0.f), 3.f), tz_);   // nearest of the 4
+                            return fmaf(dzc, dzc, fmaf(dx, dx, dy * dy)) <= A.w;
+                        };
                         const int n_lo = min(wn, 32);
-                        for (int j = 0; j < n_lo; ++j) {
-                            const float4 A = wA[j];
-                            const float dx = A.x - ox, dy = A.y - oy;
-                            const float tz_ = A.z - oz[0];
-                            const float dzc = fmaf(-resf, fminf(fmaxf(rintf(tz_ * inv_res), 0.f), 3.f), tz_);   // to the nearest of the 4
-                            const float smin = fmaf(dzc, dzc, fmaf(dx, dx, dy * dy));
-                            if (smin <= A.w) mask_lo |= 1u << j;
-                        }
-                        for (int j = 32; j < wn; ++j) {
-                            const float4 A = wA[j];
-                            const float dx = A.x - ox, dy = A.y - oy;
-                            const float tz_ = A.z - oz[0];
-                            const float dzc = fmaf(-resf, fminf(fmaxf(rintf(tz_ * inv_res), 0.f), 3.f), tz_);   // to the nearest of the 4
-                            const float smin = fmaf(dzc, dzc, fmaf(dx, dx, dy * dy));
-                            if (smin <= A.w) mask_hi |= 1u << (j - 32);
-                        }
+#pragma unroll 4
+                        for (int j = 0; j < n_lo; ++j)
+                            if (near_hit(wA[j])) mask_lo |= 1u << j;
+#pragma unroll 4
+                        for (int j = 32; j < wn; ++j)
+                            if (near_hit(wA[j])) mask_hi |= 1u << (j - 32);
                     }
                     // 3. lane-private walk over the set bits, ascending (fixed fp32 summation order)
                     while (__any_sync(0xffffffffu, (mask_lo | mask_hi) != 0u)) {

@@ -213,3 +213,48 @@ def test_random_transform_runs_and_preserves_mass():
     # rigid motion keeps every atom inside the 32 A box, so per-channel atom mass changes by < 20 %
     r = (aug.sum(dim=(2, 3, 4)) + 1) / (base.sum(dim=(2, 3, 4)) + 1)
     assert float(r.min()) > 0.8 and float(r.max()) < 1.25
+
+
+@pytest.mark.parametrize("mode", ["types", "features", "single"])
+def test_dense_cluster_overflows_staging_and_warp_lists(mode):
+    """> 512 atoms in one 8x8 column and > 64 in one cell: multi-round staging + warp-list flushes."""
+    rng = np.random.default_rng(99)
+    V = 2600
+    coords = np.concatenate([rng.normal(scale=0.6, size=(1800, 3)) + np.array([1.3, -2.1, 0.7]),
+                             rng.uniform(-9, 9, size=(V - 1800, 3))])
+    rng.shuffle(coords)
+    vox = mv.create_voxelizer(0.5, 40, "scalar", "binary", library="b200")
+    ovox = OracleVoxelizer(0.5, 40, "scalar", "binary")
+    if mode == "types":
+        types = rng.integers(0, 5, size=V)
+        out = vox.forward_types(coords, None, types, 1.0).cpu().numpy()
+        assert np.array_equal(out, ovox.forward_types(coords, None, types, 1.0))
+    elif mode == "single":
+        out = vox.forward_single(coords, None, 1.0).cpu().numpy()
+        assert np.array_equal(out, ovox.forward_single(coords, None, 1.0))
+    else:
+        feats = rng.integers(0, 4, size=(V, 20)).astype(np.float32)   # small integers: sums exact in fp32
+        out = vox.forward_features(coords, None, feats, 1.0).cpu().numpy()
+        assert np.array_equal(out, ovox.forward_features(coords, None, feats, 1.0))
+
+
+@pytest.mark.parametrize("kernel", ["rows", "cells"])
+@pytest.mark.parametrize("lpr", ["2", "4", "16"])
+def test_kernel_variants_agree_bitwise(kernel, lpr, monkeypatch):
+    """Every kernel form / cell shape gives the same bits (binary) on a mixed batch."""
+    if kernel == "rows" and lpr != "4":
+        pytest.skip("rows kernel has no cell shape")
+    monkeypatch.setenv("MVX_KERNEL", kernel)
+    monkeypatch.setenv("MVX_LPR", lpr)
+    rng = np.random.default_rng(5)
+    B = 6
+    counts = np.array([0, 3, 50, 700, 1, 1500])
+    offs = np.zeros(B + 1, dtype=np.int32)
+    offs[1:] = np.cumsum(counts)
+    coords = rng.uniform(-13, 13, size=(int(offs[-1]), 3))
+    types = rng.integers(0, 9, size=int(offs[-1]))
+    vox = mv.create_voxelizer(0.5, 48, "scalar", "binary", library="b200")
+    out = vox.forward_types_batch(coords, offs, None, types, 1.25, 9).cpu().numpy()
+    ref = oracle_forward_batch(0.5, 48, "scalar", "binary", 0.5, 8, "types", offs, coords, None, types, None, 9, 1.25,
+                               num_threads=8)
+    assert np.array_equal(out, ref)
