@@ -59,6 +59,7 @@ typedef struct mvx_grid_spec {
  *   features (N,C)  f32      feature rows, FEATURES            (:110)
  *   radius   python-float scalar when radii_type is SCALAR
  *   radii    (C,) f32 channel-wise | (N,) f32 atom-wise        (:111)
+ *   transforms (B,12) f64 optional rigid transform per molecule (:265)
  */
 typedef struct mvx_batch {
     int32_t        mode;            /* MVX_MODE_* */
@@ -78,6 +79,11 @@ typedef struct mvx_batch {
     double         max_radius;      /* host-known upper bound of every radius in `radii` (array
                                        radii types).  For FEATURES + channel-wise it must be the
                                        exact max: the reference clips with radii.max() (:138). */
+    const double  *transforms;      /* (B,12) f64 or NULL: per molecule a row-major 3x3 rotation R then a
+                                       translation t, applied to the centred coordinates as R.p + t before
+                                       the clip — the random rigid transform every reference forward_* takes
+                                       (random_translation / random_rotation, numpy/voxelizer.py:265,
+                                       numpy/transform.py:43-80), fused into the per-atom prep kernel. */
 } mvx_batch;
 
 /* Bytes of device workspace mvx_voxelize needs for this spec/batch (256-byte aligned base). */

@@ -58,6 +58,7 @@ class Batch(ctypes.Structure):
         ("radius", ctypes.c_double),
         ("radii", ctypes.c_void_p),
         ("max_radius", ctypes.c_double),
+        ("transforms", ctypes.c_void_p),
     ]
 
 

@@ -172,25 +172,31 @@ KernelChoice choose_kernel(int nv) {
     return k;
 }
 
-template <int MODE, int CH, bool BINARY, int LPR>
-cudaError_t launch_cells(const mvx::VoxParams& vp, unsigned grid, cudaStream_t st) {
-    constexpr size_t smem = mvx::cells_smem_bytes<MODE, CH>();
+template <int MODE, int CH, bool BINARY, int LPR, int NT>
+cudaError_t launch_cells_nt(const mvx::VoxParams& vp, unsigned grid, cudaStream_t st) {
+    constexpr size_t smem = mvx::cells_smem_bytes<MODE, CH, NT>();
     static bool configured = false;   // per instantiation; benign race (idempotent attribute)
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, LPR>,
+        cudaError_t e = cudaFuncSetAttribute(mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, LPR, NT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, LPR><<<grid, mvx::kThreads, smem, st>>>(vp);
+    mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, LPR, NT><<<grid, NT, smem, st>>>(vp);
     return cudaGetLastError();
+}
+
+template <int MODE, int CH, bool BINARY, int LPR>
+cudaError_t launch_cells(const mvx::VoxParams& vp, unsigned grid, cudaStream_t st) {
+    static const int nt = [] { const char* e = std::getenv("MVX_NT"); return e ? std::atoi(e) : 256; }();
+    if (nt == 128) return launch_cells_nt<MODE, CH, BINARY, LPR, 128>(vp, grid, st);
+    return launch_cells_nt<MODE, CH, BINARY, LPR, 256>(vp, grid, st);
 }
 
 template <int MODE, int CH, bool BINARY>
 cudaError_t launch_vox_nv(const mvx::VoxParams& vp, int nv, KernelChoice kc, unsigned grid, cudaStream_t st) {
     if (kc.cells && nv == 4) {
         if (kc.lpr == 4) return launch_cells<MODE, CH, BINARY, 4>(vp, grid, st);
-        if (kc.lpr == 16) return launch_cells<MODE, CH, BINARY, 16>(vp, grid, st);
         return launch_cells<MODE, CH, BINARY, 2>(vp, grid, st);  // MVX_LPR=2
     }
     if (nv == 4) mvx::mvx_voxelize_kernel<MODE, CH, BINARY, 4><<<grid, mvx::kThreads, 0, st>>>(vp);
@@ -303,7 +309,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, 
         pp.mol_offsets = batch->mol_offsets;
         pp.coords = batch->coords; pp.coords_f64 = batch->coords_dtype == MVX_F64;
         pp.centers = batch->centers; pp.centers_f64 = batch->centers_dtype == MVX_F64;
-        pp.types = batch->types; pp.radii = batch->radii;
+        pp.types = batch->types; pp.radii = batch->radii; pp.transforms = batch->transforms;
         pp.recs = recs; pp.colrange = colrange; pp.status = status;
         const unsigned grid = (unsigned)((N + 255) / 256);
         mvx::mvx_prep_kernel<<<grid, 256, 0, st>>>(pp);
@@ -398,7 +404,7 @@ int mvx_check_status(void* workspace, void* stream) {
 }
 
 namespace {
-struct Staging { size_t off_offs, off_coords, off_centers, off_types, off_features, off_radii, total; };
+struct Staging { size_t off_offs, off_coords, off_centers, off_types, off_features, off_radii, off_transforms, total; };
 void plan_staging(const mvx_grid_spec* s, const mvx_batch* b, Staging* sg) {
     const size_t N = (size_t)b->total_atoms, B = (size_t)b->num_mols;
     const size_t C = b->mode == MVX_MODE_SINGLE ? 1 : (size_t)b->num_channels;
@@ -410,6 +416,7 @@ void plan_staging(const mvx_grid_spec* s, const mvx_batch* b, Staging* sg) {
     sg->off_features = off; off += align_up(b->mode == MVX_MODE_FEATURES ? N * C * sizeof(float) : 0);
     size_t nr = s->radii_type == MVX_RADII_ATOM_WISE ? N : (s->radii_type == MVX_RADII_CHANNEL_WISE ? C : 0);
     sg->off_radii = off;    off += align_up(nr * sizeof(float));
+    sg->off_transforms = off; off += align_up(b->transforms ? B * 12 * sizeof(double) : 0);
     sg->total = off;
 }
 }  // namespace
@@ -464,6 +471,10 @@ int mvx_voxelize_host(const mvx_grid_spec* spec, const mvx_batch* hb, float* out
             MVX_CUDA_OK(cudaMemcpyAsync(dv + sg.off_radii, hb->radii, nr * sizeof(float), cudaMemcpyHostToDevice, st));
             db.radii = (const float*)(dv + sg.off_radii);
         }
+    }
+    if (hb->transforms) {
+        MVX_CUDA_OK(cudaMemcpyAsync(dv + sg.off_transforms, hb->transforms, B * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+        db.transforms = (const double*)(dv + sg.off_transforms);
     }
     rc = mvx_voxelize(spec, &db, out, workspace, pl.total, stream);
     if (rc != MVX_OK) return rc;

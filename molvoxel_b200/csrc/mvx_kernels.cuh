@@ -54,6 +54,7 @@ struct PrepParams {
     const void* centers; int centers_f64;
     const int32_t* types;
     const float* radii;
+    const double* transforms;   // (B,12) or nullptr
     AtomRec* recs;
     uint32_t* colrange;
     int* status;
@@ -117,6 +118,14 @@ __global__ void __launch_bounds__(256) mvx_prep_kernel(const PrepParams P) {
             p[k] = __dsub_rn(load_coord(P.coords, P.coords_f64, 3 * n + k),
                              load_coord(P.centers, P.centers_f64, 3 * (int64_t)mol + k));
         }
+    }
+
+    if (P.transforms != nullptr) {   // rigid augmentation about the centre: R.p + t (numpy/transform.py:43-60)
+        const double* T = P.transforms + 12 * (int64_t)mol;
+        const double q0 = T[0] * p[0] + T[1] * p[1] + T[2] * p[2] + T[9];
+        const double q1 = T[3] * p[0] + T[4] * p[1] + T[5] * p[2] + T[10];
+        const double q2 = T[6] * p[0] + T[7] * p[1] + T[8] * p[2] + T[11];
+        p[0] = q0; p[1] = q1; p[2] = q2;
     }
 
     bool keep = true;
@@ -489,22 +498,23 @@ __global__ void __launch_bounds__(kThreads) mvx_voxelize_kernel(const VoxParams 
 //      any lane — this removes the SIMT divergence that bounded the dense (protein) workloads.
 // Zero fill of empty columns is division-free: one address computation per thread item.
 // ---------------------------------------------------------------------------------------------
-constexpr int kStageCap = 512;   // candidates staged per round
 constexpr int kWarpList = 64;    // warp-private list capacity (two 32-bit hit masks)
 constexpr uint32_t kNoForb = 0xFFFFFFFFu;
 
 template <int CH>
 __host__ __device__ constexpr int feat_stride() { return CH + 4; }   // +4 words: conflict-free lane-private LDS.128
 
-template <int MODE, int CH>
+template <int MODE, int CH, int NT>
 constexpr size_t cells_smem_bytes() {
-    return (size_t)kStageCap * (2 * sizeof(float4) + sizeof(int) + sizeof(uint32_t)) +
-           8 * kWarpList * (2 * sizeof(float4) + sizeof(uint16_t)) + 32 * sizeof(float4) +
-           (MODE == 2 ? (size_t)kStageCap * feat_stride<CH>() * sizeof(float) : 0);
+    return (size_t)(2 * NT) * (2 * sizeof(float4) + sizeof(int) + sizeof(uint32_t)) +
+           (NT / 32) * kWarpList * (2 * sizeof(float4) + sizeof(uint16_t)) + 32 * sizeof(float4) +
+           (MODE == 2 ? (size_t)(2 * NT) * feat_stride<CH>() * sizeof(float) : 0);
 }
 
-template <int MODE, int CH, bool BINARY, int LPR>
-__global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cells_kernel(const VoxParams P) {
+template <int MODE, int CH, bool BINARY, int LPR, int NT>
+__global__ void __launch_bounds__(NT, (CH <= 8 ? 3 : 2) * (256 / NT)) mvx_voxelize_cells_kernel(const VoxParams P) {
+    constexpr int NW = NT / 32;   // warps per CTA
+    constexpr int SC = 2 * NT;    // atoms staged per round
     constexpr int ROWS = 32 / LPR;
     constexpr int RY = (LPR >= 8) ? 2 : 4;
     constexpr int RX = ROWS / RY;
@@ -515,14 +525,14 @@ __global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cell
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* sA = reinterpret_cast<float4*>(smem_raw);        // rel x, rel y, rel z, r^2 + tau
-    float4* sB = sA + kStageCap;                             // r^2 - tau, gaussian coef, forbidden planes, type | radius
-    int* sN = reinterpret_cast<int*>(sB + kStageCap);        // global atom id (exact recheck)
-    uint32_t* sM = reinterpret_cast<uint32_t*>(sN + kStageCap);   // cells reached by the cutoff sphere
-    float4* wA_all = reinterpret_cast<float4*>(sM + kStageCap);
-    float4* wB_all = wA_all + 8 * kWarpList;
-    uint16_t* wI_all = reinterpret_cast<uint16_t*>(wB_all + 8 * kWarpList);
-    float4* sBox = reinterpret_cast<float4*>(wI_all + 8 * kWarpList);   // per cell: box centre x, y, z, half z
-    float* sF = reinterpret_cast<float*>(sBox + 32);               // features [kStageCap][CH + 4]
+    float4* sB = sA + SC;                             // r^2 - tau, gaussian coef, forbidden planes, type | radius
+    int* sN = reinterpret_cast<int*>(sB + SC);        // global atom id (exact recheck)
+    uint32_t* sM = reinterpret_cast<uint32_t*>(sN + SC);   // cells reached by the cutoff sphere
+    float4* wA_all = reinterpret_cast<float4*>(sM + SC);
+    float4* wB_all = wA_all + NW * kWarpList;
+    uint16_t* wI_all = reinterpret_cast<uint16_t*>(wB_all + NW * kWarpList);
+    float4* sBox = reinterpret_cast<float4*>(wI_all + NW * kWarpList);   // per cell: box centre x, y, z, half z
+    float* sF = reinterpret_cast<float*>(sBox + 32);               // features [SC][CH + 4]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int t = blockIdx.x;
@@ -541,10 +551,10 @@ __global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cell
     if (cnt == 0) {   // empty column: pure zero fill, one address computation per thread item
         const int lz = (z1 - z0) >> 2;
         const int nitems = kTile * kTile * lz;
-        const int qstep = kThreads / lz, rstep = kThreads - qstep * lz;
+        const int qstep = NT / lz, rstep = NT - qstep * lz;
         int row = tid / lz, lzi = tid - row * lz;
         const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int item = tid; item < nitems; item += kThreads) {
+        for (int item = tid; item < nitems; item += NT) {
             const int x = x0 + (row >> 3), y = y0 + (row & 7);
             if (x < D && y < D) {
                 float* p = out_mol + (size_t)P.c_begin * plane + ((size_t)x * D + y) * D + z0 + lzi * 4;
@@ -561,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cell
     const double oy0 = (double)y0 * P.res - P.half_width;
     const double oz0 = (double)z0 * P.res - P.half_width;
     const float resf = (float)P.res;
-    const bool single_round = cnt <= kStageCap;
+    const bool single_round = cnt <= SC;
     int staged_c0 = -1;
 
     float4* wA = wA_all + warp * kWarpList;
@@ -583,7 +593,7 @@ __global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cell
     }
 
     for (int c0 = P.c_begin; c0 < P.c_end; c0 += CH) {
-        for (int cell0 = 0; cell0 < ncells; cell0 += 8) {
+        for (int cell0 = 0; cell0 < ncells; cell0 += NW) {
             const int cell = cell0 + warp;
             const bool cell_ok = cell < ncells;
             const int cz = cell / (NCX * NCY), cxy = cell % (NCX * NCY);
@@ -603,11 +613,11 @@ __global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cell
 #pragma unroll
                 for (int k = 0; k < 4; ++k) acc[c][k] = 0.f;
 
-            for (int r0 = 0; r0 < cnt; r0 += kStageCap) {
-                const int nc = min(kStageCap, cnt - r0);
+            for (int r0 = 0; r0 < cnt; r0 += SC) {
+                const int nc = min(SC, cnt - r0);
                 if (!(single_round && staged_c0 == c0)) {
                     __syncthreads();
-                    for (int i = tid; i < nc; i += kThreads) {
+                    for (int i = tid; i < nc; i += NT) {
                         const int n = (int)list[r0 + i];
                         const AtomRec rec = P.recs[n];
                         float r = rec.r;
@@ -628,7 +638,7 @@ __global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cell
                         sN[i] = n;
                     }
                     if (MODE == 2) {
-                        for (int i = tid; i < nc * CH; i += kThreads) {
+                        for (int i = tid; i < nc * CH; i += NT) {
                             const int j = i / CH, c = i - j * CH;
                             const int n = (int)list[r0 + j];
                             sF[j * FS + c] = (c0 + c < P.C) ? P.features[(size_t)n * P.C + c0 + c] : 0.f;
@@ -639,7 +649,7 @@ __global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cell
                     // test; the ballot IS the atom's 32-bit mask of cells its cutoff sphere reaches
                     {
                         const float4 box = sBox[lane];
-                        for (int i = warp; i < nc; i += kThreads / 32) {
+                        for (int i = warp; i < nc; i += NW) {
                             const float4 A = sA[i];
                             const float ex = fmaxf(fabsf(A.x - box.x) - bhx, 0.f);
                             const float ey = fmaxf(fabsf(A.y - box.y) - bhy, 0.f);

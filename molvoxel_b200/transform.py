@@ -49,6 +49,16 @@ def random_transform_params(num_mols, random_translation, random_rotation):
     return [_draw(random_translation, random_rotation) for _ in range(num_mols)]
 
 
+def transform_matrix_array(params) -> np.ndarray:
+    """(B, 12) float64 for the C ABI: row-major rotation (identity if None) followed by the translation."""
+    out = np.zeros((len(params), 12), dtype=np.float64)
+    for m, (rot, tr) in enumerate(params):
+        out[m, :9] = (np.eye(3) if rot is None else rot).reshape(-1)
+        if tr is not None:
+            out[m, 9:] = np.asarray(tr, dtype=np.float64).reshape(-1)
+    return out
+
+
 def _apply_one(xyz, center, rot, tr):
     lib = torch if isinstance(xyz, torch.Tensor) else np
     if isinstance(xyz, torch.Tensor):

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .transform import RandomTransform, random_transform_params, apply_transform
+from .transform import RandomTransform, random_transform_params, transform_matrix_array
 
 
 def _norm(x):
@@ -66,6 +66,7 @@ class Voxelizer:
         if self.device.type == "cuda" and self.device.index is None and torch.cuda.is_available():
             self.device = torch.device("cuda", torch.cuda.current_device())
         self._ws = None
+        self._pipe = None
         _lib.lib()   # fail loudly here if the CUDA library cannot be built/loaded
 
     # ---- properties of the reference contract (base/voxelizer.py:40-97) ----
@@ -223,19 +224,25 @@ class Voxelizer:
 
     # ---- batched driver (new, additive; per-molecule semantics = B independent reference calls) ----
     def forward_types_batch(self, coords, mol_offsets, centers, types, radii, num_channels,
-                            random_translation: float = 0.0, random_rotation: bool = False, out=None):
+                            random_translation: float = 0.0, random_rotation: bool = False, out=None,
+                            non_blocking: bool = False):
+        """CSR batch -> (B, C, D, H, W).  non_blocking=True with HOST inputs pipelines the H2D copies of this
+        call behind the kernels of the previous one (pinned inputs; call check_status() to synchronise)."""
         return self._forward_batch("types", coords, mol_offsets, centers, types, radii, int(num_channels),
-                                   random_translation, random_rotation, out)
+                                   random_translation, random_rotation, out, non_blocking=non_blocking)
 
     def forward_features_batch(self, coords, mol_offsets, centers, features, radii,
-                               random_translation: float = 0.0, random_rotation: bool = False, out=None):
+                               random_translation: float = 0.0, random_rotation: bool = False, out=None,
+                               non_blocking: bool = False):
         return self._forward_batch("features", coords, mol_offsets, centers, features, radii,
-                                   int(features.shape[1]), random_translation, random_rotation, out)
+                                   int(features.shape[1]), random_translation, random_rotation, out,
+                                   non_blocking=non_blocking)
 
     def forward_single_batch(self, coords, mol_offsets, centers, radii,
-                             random_translation: float = 0.0, random_rotation: bool = False, out=None):
+                             random_translation: float = 0.0, random_rotation: bool = False, out=None,
+                             non_blocking: bool = False):
         return self._forward_batch("single", coords, mol_offsets, centers, None, radii, 1,
-                                   random_translation, random_rotation, out)
+                                   random_translation, random_rotation, out, non_blocking=non_blocking)
 
     # ---- implementation ----
     def _spec(self):
@@ -261,12 +268,61 @@ class Voxelizer:
             assert tuple(radii.shape) == (V,), \
                 f"radii does not match dimension (number of atoms,): {tuple(radii.shape)} vs {(V,)}"
 
+    def _upload_pipelined(self, arrays):
+        """H2D of one call's host inputs on the copy stream into this call's slot of a 2-deep ring of device
+        staging tensors; the compute stream waits on the copy, and the slot is reused only after the kernels
+        that read it have finished.  Returns device tensors in the order given."""
+        if self._pipe is None:
+            self._pipe = {"copy": torch.cuda.Stream(self.device), "idx": 0,
+                          "slots": [{"bufs": {}, "copied": torch.cuda.Event(), "done": torch.cuda.Event()} for _ in range(2)],
+                          "status": torch.zeros(2, dtype=torch.int32).pin_memory()}
+        pipe = self._pipe
+        slot = pipe["slots"][pipe["idx"]]
+        slot["index"] = pipe["idx"]
+        pipe["idx"] ^= 1
+        slot["done"].synchronize()
+        cur = torch.cuda.current_stream(self.device)
+        outs = []
+        with torch.cuda.stream(pipe["copy"]):
+            for name, a in arrays:
+                if a is None:
+                    outs.append(None)
+                    continue
+                src = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+                buf = slot["bufs"].get(name)
+                if buf is None or buf.dtype != src.dtype or buf.numel() < src.numel():
+                    buf = torch.empty(max(src.numel(), 1), dtype=src.dtype, device=self.device)
+                    slot["bufs"][name] = buf
+                dst = buf[:src.numel()].view(src.shape)
+                dst.copy_(src, non_blocking=True)
+                outs.append(dst)
+            slot["copied"].record(pipe["copy"])
+        cur.wait_event(slot["copied"])
+        return outs, slot
+
     def _forward_batch(self, mode, coords, mol_offsets, centers, channels, radii, C, random_translation,
-                       random_rotation, out, infer_types_channels=False, max_radius=None):
+                       random_rotation, out, infer_types_channels=False, max_radius=None, non_blocking=False):
         if self.device.type != "cuda" or not torch.cuda.is_available():
             raise RuntimeError("molvoxel_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         coords, centers, channels, radii = _norm(coords), _norm(centers), _norm(channels), _norm(radii)
         on_device = isinstance(coords, torch.Tensor) and coords.is_cuda
+        if non_blocking and not on_device:
+            # pipelined host path: async H2D on the copy stream, then the no-sync device path
+            if not _is_scalar(radii) and max_radius is None:
+                max_radius = float(np.asarray(radii).max()) if np.asarray(radii).size else 1.0
+            if mode == "types" and C is None:
+                C = int(np.asarray(channels).max()) + 1
+            (coords_d, offs_d, centers_d, chan_d, radii_d), slot = self._upload_pipelined([
+                ("coords", coords), ("offs", np.asarray(mol_offsets, dtype=np.int32) if not isinstance(mol_offsets, torch.Tensor) else mol_offsets),
+                ("centers", centers), ("chan", channels), ("radii", None if _is_scalar(radii) else radii)])
+            res = self._forward_batch(mode, coords_d, offs_d, centers_d, chan_d, radii if _is_scalar(radii) else radii_d, C,
+                                      random_translation, random_rotation, out, False, max_radius)
+            cur = torch.cuda.current_stream(self.device)
+            ws_ptr_off = (-self._ws.data_ptr()) % 256
+            self._pipe["status"][slot["index"]:slot["index"] + 1].copy_(
+                self._ws[ws_ptr_off:ws_ptr_off + 4].view(torch.int32), non_blocking=True)
+            slot["done"].record(cur)
+            return res
         D = self._dimension
         N = int(coords.shape[0])
         assert coords.ndim == 2 and coords.shape[1] == 3, f"coords should be (V, 3): {tuple(coords.shape)}"
@@ -317,9 +373,9 @@ class Voxelizer:
 
         # centring stays inside the kernel (fp64 or numpy's fp32-fp32 promotion); the optional random
         # rigid transform is applied to centred coordinates first, like the reference (numpy/voxelizer.py:263-265)
+        transforms = None
         if (random_translation is not None and random_translation > 0.0) or random_rotation:
-            coords, centers = apply_transform(coords, mol_offsets, centers,
-                                              random_transform_params(B, random_translation, random_rotation))
+            transforms = transform_matrix_array(random_transform_params(B, random_translation, random_rotation))
 
         keep = []   # keeps converted arrays alive until the call returns
 
@@ -363,6 +419,8 @@ class Voxelizer:
                 r = dev(torch.as_tensor(radii), torch.float32)
                 b.radii = ptr(r)
                 b.max_radius = float(max_radius) if max_radius is not None else (float(r.max()) if r.numel() else 1.0)
+            if transforms is not None:
+                b.transforms = ptr(dev(torch.from_numpy(transforms), torch.float64))
         else:
             ptr = lambda a: ctypes.c_void_p(a.ctypes.data)   # noqa: E731
             b.mol_offsets = ptr(host(mol_offsets, np.int32))
@@ -384,6 +442,8 @@ class Voxelizer:
                 r = host(radii, np.float32)
                 b.radii = ptr(r)
                 b.max_radius = float(max_radius) if max_radius is not None else (float(r.max()) if r.size else 1.0)
+            if transforms is not None:
+                b.transforms = ptr(host(transforms, np.float64))
 
         L = _lib.lib()
         spec = self._spec()
@@ -417,3 +477,10 @@ class Voxelizer:
         with torch.cuda.device(self.device):
             stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             _lib.raise_for_status(_lib.lib().mvx_check_status(ctypes.c_void_p(ws_ptr), stream))
+        if self._pipe is not None:   # status words copied back by the pipelined (non_blocking) calls
+            flags = int(self._pipe["status"][0]) | int(self._pipe["status"][1])
+            self._pipe["status"].zero_()
+            if flags & 1:
+                raise ValueError("a type index is outside [0, num_channels)")
+            if flags & 2:
+                raise ValueError("a radius exceeds max_radius")

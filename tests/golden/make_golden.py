@@ -201,6 +201,24 @@ def main():
               dict(mode="types", resolution=0.5, dimension=48, radii_type="scalar", density_type="binary", blockdim=None),
               coords, np.zeros(3), rng.integers(0, 4, size=V).astype(np.int16), 1.0)
 
+    # other blockdim values: the cull emulation must hold for any block size (non-divisors, 1-voxel blocks)
+    rng2 = np.random.default_rng(77)
+    for bd in (5, 16, 3, 1):
+        coords = synth(rng2, 250, 24, 0.5, spread=1.5)
+        types = rng2.integers(0, 4, size=250).astype(np.int16)
+        save_case(f"d24_bd{bd}_types_binary",
+                  dict(mode="types", resolution=0.5, dimension=24, radii_type="scalar", density_type="binary", blockdim=bd),
+                  coords, None, types, 1.2)
+        save_case(f"d24_bd{bd}_feat_atom_gaussian",
+                  dict(mode="features", resolution=0.5, dimension=24, radii_type="atom-wise", density_type="gaussian", blockdim=bd),
+                  coords, rng2.uniform(-0.2, 0.2, size=3), rng2.uniform(0, 1, size=(250, 5)).astype(np.float32),
+                  rng2.uniform(0.7, 2.2, size=250).astype(np.float32))
+    # resolution that is not exactly representable in fp32, 96-wide grid split in two z chunks, large radii
+    coords = synth(rng2, 600, 96, 0.3, spread=1.0)
+    save_case("d96_res03_types_atom_binary",
+              dict(mode="types", resolution=0.3, dimension=96, radii_type="atom-wise", density_type="binary", blockdim=None),
+              coords, None, rng2.integers(0, 3, size=600).astype(np.int16), rng2.uniform(0.6, 2.5, size=600).astype(np.float32))
+
     json.dump({"molvoxel": molvoxel.__version__, "numpy": np.__version__, "scipy": scipy.__version__,
                "python": sys.version.split()[0], "backend": "numpy precision=32"},
               open(os.path.join(HERE, "versions.json"), "w"), indent=1)

@@ -258,3 +258,43 @@ def test_kernel_variants_agree_bitwise(kernel, lpr, monkeypatch):
     ref = oracle_forward_batch(0.5, 48, "scalar", "binary", 0.5, 8, "types", offs, coords, None, types, None, 9, 1.25,
                                num_threads=8)
     assert np.array_equal(out, ref)
+
+
+def test_fused_random_transform_matches_host_transform():
+    """The transform fused into the prep kernel == transforming on the host and voxelizing the result."""
+    from molvoxel_b200.transform import apply_transform, random_transform_params
+    rng = np.random.default_rng(21)
+    offs, coords, types = ligand_batch(rng, 12, 4)
+    centers = rng.normal(scale=0.5, size=(12, 3))
+    vox = mv.create_voxelizer(0.5, 64, "scalar", "gaussian", library="b200")
+    np.random.seed(7)
+    aug = vox.forward_types_batch(coords, offs, centers, types, 1.0, 4, random_translation=0.5, random_rotation=True)
+    np.random.seed(7)
+    moved, _ = apply_transform(coords, offs, centers, random_transform_params(12, 0.5, True))
+    ref = oracle_forward_batch(0.5, 64, "scalar", "gaussian", 0.5, 8, "types", offs, moved, None, types, None, 4, 1.0,
+                               num_threads=8)
+    got = aug.cpu().numpy()
+    assert float(np.abs(got - ref).max()) <= 0.14   # at most a cutoff tie flipped by 1e-16 coordinate noise ...
+    assert (np.abs(got - ref) > 1e-5).sum() <= 2     # ... in at most a couple of voxels
+
+
+def test_pipelined_host_path_matches_blocking():
+    rng = np.random.default_rng(8)
+    vox = mv.create_voxelizer(0.5, 32, "atom-wise", "gaussian", library="b200")
+    outs_a, outs_b = [], []
+    batches = []
+    for k in range(5):
+        offs, coords, types = ligand_batch(rng, 6, 5, 20, 30)
+        radii = rng.uniform(0.8, 1.6, size=coords.shape[0]).astype(np.float32)
+        batches.append((coords, offs, types, radii))
+    for coords, offs, types, radii in batches:
+        outs_a.append(vox.forward_types_batch(coords, offs, None, types, radii, 5, non_blocking=True).clone())
+    vox.check_status()
+    for coords, offs, types, radii in batches:
+        outs_b.append(vox.forward_types_batch(coords, offs, None, types, radii, 5))
+    for a, b in zip(outs_a, outs_b):
+        assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        coords, offs, types, radii = batches[0]
+        vox.forward_types_batch(coords, offs, None, types + 7, radii, 5, non_blocking=True)
+        vox.check_status()
