@@ -48,7 +48,8 @@ struct Plan {
     int ncol, nzc, tz, maxcols, nv;
     float tau_lin, tau_quad;
     // workspace offsets (bytes)
-    size_t off_status, off_recs, off_colrange, off_bins, off_lists, total;
+    size_t off_status, off_recs, off_colrange, off_bins, off_lists, off_entries, total;
+    int masks;   // expand pass precomputes the cell masks (<= 64 cells per column)
 };
 
 int check_args(const mvx_grid_spec* s, const mvx_batch* b) {
@@ -141,7 +142,8 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     pl->tz = tz;
     pl->nzc = (D + tz - 1) / tz;
     // tolerance band of the fp32 cutoff test (see DESIGN.md "cutoff decisions")
-    const double ext = (double)(tz > mvx::kTile ? tz : mvx::kTile) * s->resolution + reach;
+    // coordinates are column-relative in x, y and grid-relative in z (ColEntry), so the extent is the grid's
+    const double ext = (double)D * s->resolution + reach;
     pl->tau_lin = (float)(21.0 * std::ldexp(1.0, -24) * ext);
     pl->tau_quad = (float)(12.0 * std::ldexp(1.0, -24));
 
@@ -152,6 +154,8 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     pl->off_colrange = off; off += align_up(N * sizeof(uint32_t));
     pl->off_bins = off;     off += align_up(B * (size_t)pl->ncol * sizeof(uint2));
     pl->off_lists = off;    off += align_up(N * (size_t)pl->maxcols * sizeof(uint32_t));
+    pl->off_entries = off;  off += align_up(pl->nv == 4 ? N * (size_t)pl->maxcols * sizeof(mvx::ColEntry) : 0);
+    pl->masks = pl->nzc * ((tz + mvx::kCellZ - 1) / mvx::kCellZ) * mvx::kCellsXY <= 64;
     pl->total = off;
     return MVX_OK;
 }
@@ -275,7 +279,8 @@ int mvx_launches_per_call(const mvx_grid_spec* spec, const mvx_batch* batch) {
     const bool chan_feat = batch->mode == MVX_MODE_FEATURES && spec->radii_type == MVX_RADII_CHANNEL_WISE;
     int nvox = chan_feat ? batch->num_channels : 1;
     const int nbin = bin_groups(batch->num_mols, pl.ncol) <= 1 ? 1 : 2;
-    return (batch->total_atoms > 0 ? 1 : 0) + nbin + nvox;   // prep + bin + voxelize
+    const int nexp = (choose_kernel(pl.nv).cells && batch->total_atoms > 0) ? 1 : 0;
+    return (batch->total_atoms > 0 ? 1 : 0) + nbin + nexp + nvox;   // prep + bin + expand + voxelize
 }
 
 int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, void* workspace,
@@ -295,6 +300,8 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, 
     uint32_t* colrange = (uint32_t*)(ws + pl.off_colrange);
     uint2* bins = (uint2*)(ws + pl.off_bins);
     uint32_t* lists = (uint32_t*)(ws + pl.off_lists);
+    mvx::ColEntry* entries = (mvx::ColEntry*)(ws + pl.off_entries);
+    const KernelChoice kchoice = choose_kernel(pl.nv);
 
     const int B = batch->num_mols;
     const int64_t N = batch->total_atoms;
@@ -330,6 +337,18 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, 
             mvx::mvx_bin_fill_kernel<<<(unsigned)(B * groups), 256, smem, st>>>(bp, groups);
         }
         MVX_CUDA_OK(cudaGetLastError());
+        if (kchoice.cells && N > 0) {   // column lists -> staged-ready entries for the warp-cell kernel
+            mvx::ExpandParams ep;
+            ep.res = pl.geo.res; ep.half_width = pl.geo.half_width; ep.sigma = spec->sigma;
+            ep.tau_lin = pl.tau_lin; ep.tau_quad = pl.tau_quad;
+            ep.dim = spec->dimension; ep.ncx = pl.geo.ncx; ep.ncol = pl.ncol; ep.nzc = pl.nzc; ep.tz = pl.tz;
+            ep.maxcols = pl.maxcols; ep.mode = batch->mode; ep.masks = pl.masks && kchoice.lpr == 4; ep.B = B;
+            ep.mol_offsets = batch->mol_offsets; ep.recs = recs; ep.bins = bins; ep.lists = lists;
+            ep.types = batch->types; ep.entries = entries;
+            const long long warps = (long long)B * pl.ncol;
+            mvx::mvx_expand_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(ep);
+            MVX_CUDA_OK(cudaGetLastError());
+        }
     }
     prof_mark(st, 2);
     {
@@ -340,6 +359,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, 
         vp.C = C; vp.Cout = batch->out_channels; vp.maxcols = pl.maxcols; vp.cull = pl.geo.nb > 1;
         vp.mol_offsets = batch->mol_offsets; vp.recs = recs; vp.bins = bins; vp.lists = lists;
         vp.types = batch->types; vp.features = batch->features; vp.chan_radii = nullptr; vp.out = out;
+        vp.entries = entries; vp.masks = pl.masks && kchoice.lpr == 4;
         const unsigned long long nblk = (unsigned long long)B * pl.ncol * pl.nzc;
         if (nblk > 0x7fffffffULL) return fail(MVX_ERR_BAD_SHAPE, "batch too large for one launch; split it");
         const bool binary = spec->density_type == MVX_DENSITY_BINARY;

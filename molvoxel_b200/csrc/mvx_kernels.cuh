@@ -68,6 +68,34 @@ struct BinParams {
     uint32_t* lists;    // molecule m owns [mol_offsets[m]*maxcols, mol_offsets[m+1]*maxcols)
 };
 
+// One atom as seen from one 8x8 voxel column, ready for the voxelize kernel's shared-memory staging (48 B).
+struct __align__(16) ColEntry {
+    float ax, ay, az, r2hi;     // position relative to (column x0, column y0, grid z = 0);  r^2 + tau
+    float r2lo, kc;             // r^2 - tau;  -0.5*log2(e)/(r*sigma)^2
+    uint32_t forb;              // forbidden planes: fx | fy << 8 (column-relative, 0xFF none) | fz << 16 (absolute, 0xFFFF none)
+    uint32_t type_or_r;         // TYPES: channel index;  else: fp32 radius bits
+    uint32_t n;                 // global atom id (features row, exact recheck)
+    uint32_t mask_lo, mask_hi;  // cells (layer * 8 + cx * 2 + cy) whose voxel-centre box the cutoff sphere reaches
+    uint32_t pad;
+};
+static_assert(sizeof(ColEntry) == 48, "ColEntry layout");
+
+// cell shape of the warp-cell kernel: 2 x 4 x 16 voxels (4 lanes of one float4 along z per row)
+constexpr int kCellX = 2, kCellY = 4, kCellZ = 16;
+constexpr int kCellsXY = (kTile / kCellX) * (kTile / kCellY);   // 8 cells per z layer of a tile
+
+struct ExpandParams {
+    double res, half_width, sigma;
+    float tau_lin, tau_quad;
+    int dim, ncx, ncol, nzc, tz, maxcols, mode, masks, B;
+    const int32_t* mol_offsets;
+    const AtomRec* recs;
+    const uint2* bins;
+    const uint32_t* lists;
+    const int32_t* types;
+    ColEntry* entries;
+};
+
 struct VoxParams {
     double res, half_width, sigma;
     float tau_lin, tau_quad;
@@ -82,6 +110,8 @@ struct VoxParams {
     const int32_t* types;
     const float* features;
     const float* chan_radii;   // channel-wise features: kernel radius of channel c_begin
+    const ColEntry* entries;   // expanded column lists (warp-cell kernel)
+    int masks;                 // 1: entries carry precomputed cell masks
     float* out;
 };
 
@@ -299,6 +329,77 @@ __global__ void mvx_bin_fill_kernel(const BinParams P, int groups) {
     for (int col = grp * nwarps + warp; col < P.ncol; col += groups * nwarps) {
         if (s_cnt[col] != 0) bin_scan_column(cr, V, col / P.ncx, col % P.ncx, lane, seg, s_off[col], a0);
         if (lane == 0) P.bins[(size_t)mol * P.ncol + col].x = s_off[col];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// expand: one warp per (molecule, column), one lane per list entry.  Turns the atom ids of a column list
+// into ColEntry records (column-relative fp32 position from the fp64 record, cutoff band, Gaussian
+// coefficient, packed forbidden planes, and the mask of warp cells the cutoff sphere reaches), so that the
+// voxelize kernel stages a column with one coalesced copy and no per-atom arithmetic.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mvx_expand_kernel(const ExpandParams P) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gw >= (long long)P.B * P.ncol) return;
+    const int mol = (int)(gw / P.ncol), col = (int)(gw % P.ncol);
+    const uint2 bin = P.bins[gw];
+    if (bin.y == 0) return;
+    const size_t base = (size_t)P.mol_offsets[mol] * (size_t)P.maxcols + bin.x;
+    const int x0 = (col / P.ncx) * kTile, y0 = (col % P.ncx) * kTile;
+    const double ox0 = (double)x0 * P.res - P.half_width, oy0 = (double)y0 * P.res - P.half_width;
+    const float resf = (float)P.res;
+    const float bhx = 0.5f * (kCellX - 1) * resf, bhy = 0.5f * (kCellY - 1) * resf;
+    const int ncz_max = (P.tz + kCellZ - 1) / kCellZ;
+    for (uint32_t i = lane; i < bin.y; i += 32) {
+        const uint32_t n = P.lists[base + i];
+        const AtomRec rec = P.recs[n];
+        const float r = rec.r;
+        const float r2 = r * r;
+        const float tau = r * P.tau_lin + r2 * P.tau_quad;
+        ColEntry e;
+        e.ax = (float)(rec.px - ox0); e.ay = (float)(rec.py - oy0); e.az = (float)(rec.pz + P.half_width);
+        e.r2hi = r2 + tau; e.r2lo = r2 - tau;
+        const double rs = (double)r * P.sigma;
+        e.kc = (float)(-0.5 * 1.4426950408889634 / (rs * rs));
+        const int fx = rec.fx - x0, fy = rec.fy - y0;
+        e.forb = (uint32_t)((rec.fx >= 0 && fx >= 0 && fx < kTile) ? fx : 0xFF) |
+                 ((uint32_t)((rec.fy >= 0 && fy >= 0 && fy < kTile) ? fy : 0xFF) << 8) |
+                 ((uint32_t)(rec.fz >= 0 ? rec.fz : 0xFFFF) << 16);
+        e.type_or_r = (P.mode == 1) ? (uint32_t)P.types[n] : __float_as_uint(r);
+        e.n = n; e.pad = 0;
+        unsigned long long mask = 0ull;
+        if (P.masks) {
+            const float lim = e.r2hi + 1e-4f * (1.f + e.r2hi);
+            for (int zc = 0; zc < P.nzc; ++zc) {
+                const int z0 = zc * P.tz, z1 = min(P.dim, z0 + P.tz);
+                if (rec.zhi < z0 || rec.zlo >= z1) continue;
+                for (int cz = 0; cz < ncz_max; ++cz) {
+                    const int lo = z0 + cz * kCellZ;
+                    if (lo >= z1) break;
+                    const float bhz = 0.5f * (min(kCellZ, z1 - lo) - 1) * resf;
+                    const float ez = fmaxf(fabsf(e.az - (lo * resf + bhz)) - bhz, 0.f);
+                    const float ez2 = ez * ez;
+                    if (ez2 > lim) continue;
+                    const int layer = zc * ncz_max + cz;
+#pragma unroll
+                    for (int ix = 0; ix < kTile / kCellX; ++ix) {
+                        const float ex = fmaxf(fabsf(e.ax - ((ix * kCellX) * resf + bhx)) - bhx, 0.f);
+                        const float exz = fmaf(ex, ex, ez2);
+                        if (exz > lim) continue;
+#pragma unroll
+                        for (int iy = 0; iy < kTile / kCellY; ++iy) {
+                            const float ey = fmaxf(fabsf(e.ay - ((iy * kCellY) * resf + bhy)) - bhy, 0.f);
+                            if (fmaf(ey, ey, exz) <= lim) mask |= 1ull << (layer * kCellsXY + ix * (kTile / kCellY) + iy);
+                        }
+                    }
+                }
+            }
+        }
+        e.mask_lo = (uint32_t)mask; e.mask_hi = (uint32_t)(mask >> 32);
+        float4* dst = reinterpret_cast<float4*>(P.entries + base + i);
+        const float4* src = reinterpret_cast<const float4*>(&e);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
     }
 }
 
@@ -566,11 +667,9 @@ __global__ void __launch_bounds__(NT, (CH <= 8 ? 3 : 2) * (256 / NT)) mvx_voxeli
         return;
     }
 
-    const uint32_t* list = P.lists + (size_t)P.mol_offsets[mol] * (size_t)P.maxcols + bin.x;
-    const double ox0 = (double)x0 * P.res - P.half_width;
-    const double oy0 = (double)y0 * P.res - P.half_width;
-    const double oz0 = (double)z0 * P.res - P.half_width;
+    const ColEntry* ent = P.entries + (size_t)P.mol_offsets[mol] * (size_t)P.maxcols + bin.x;
     const float resf = (float)P.res;
+    const int mask_shift = zc * ((P.tz + CZ - 1) / CZ) * (NCX * NCY);
     const bool single_round = cnt <= SC;
     int staged_c0 = -1;
 
@@ -589,7 +688,7 @@ __global__ void __launch_bounds__(NT, (CH <= 8 ? 3 : 2) * (256 / NT)) mvx_voxeli
         const int bz = tid / (NCX * NCY), bxy = tid % (NCX * NCY);
         const int czn = max(1, min(CZ, z1 - z0 - bz * CZ));
         const float bhz = 0.5f * (czn - 1) * resf;
-        sBox[tid] = make_float4(((bxy / NCY) * RX) * resf + bhx, ((bxy % NCY) * RY) * resf + bhy, (bz * CZ) * resf + bhz, bhz);
+        sBox[tid] = make_float4(((bxy / NCY) * RX) * resf + bhx, ((bxy % NCY) * RY) * resf + bhy, (z0 + bz * CZ) * resf + bhz, bhz);
     }
 
     for (int c0 = P.c_begin; c0 < P.c_end; c0 += CH) {
@@ -605,7 +704,7 @@ __global__ void __launch_bounds__(NT, (CH <= 8 ? 3 : 2) * (256 / NT)) mvx_voxeli
             const float ox = (float)((double)lx * P.res), oy = (float)((double)ly * P.res);
             float oz[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) oz[k] = (float)((double)(lzv + k) * P.res);
+            for (int k = 0; k < 4; ++k) oz[k] = (float)((double)(z + k) * P.res);   // grid-absolute, like ColEntry::az
 
             float acc[CH][4];
 #pragma unroll
@@ -617,37 +716,36 @@ __global__ void __launch_bounds__(NT, (CH <= 8 ? 3 : 2) * (256 / NT)) mvx_voxeli
                 const int nc = min(SC, cnt - r0);
                 if (!(single_round && staged_c0 == c0)) {
                     __syncthreads();
-                    for (int i = tid; i < nc; i += NT) {
-                        const int n = (int)list[r0 + i];
-                        const AtomRec rec = P.recs[n];
-                        float r = rec.r;
-                        if (MODE == 2 && P.chan_radii != nullptr) r = P.chan_radii[c0];
-                        const float r2 = r * r;
-                        const float tau = r * P.tau_lin + r2 * P.tau_quad;
-                        const float r2hi = r2 + tau;
-                        const int fx = rec.fx - x0, fy = rec.fy - y0, fz = rec.fz - z0;
-                        const uint32_t forb = (uint32_t)((rec.fx >= 0 && fx >= 0 && fx < kTile) ? fx : 0xFF) |
-                                              ((uint32_t)((rec.fy >= 0 && fy >= 0 && fy < kTile) ? fy : 0xFF) << 8) |
-                                              ((uint32_t)((rec.fz >= 0 && fz >= 0 && fz < 0xFFFF) ? fz : 0xFFFF) << 16);
-                        const double rs = (double)r * P.sigma;
-                        const float kc = (float)(-0.5 * 1.4426950408889634 / (rs * rs));
-                        const float ax = (float)(rec.px - ox0), ay = (float)(rec.py - oy0), az = (float)(rec.pz - oz0);
-                        const bool z_out = rec.zhi < z0 || rec.zlo >= z1;   // outside this z chunk: reaches no cell
-                        sA[i] = make_float4(ax, ay, az, z_out ? -1.f : r2hi);
-                        sB[i] = make_float4(r2 - tau, kc, __uint_as_float(forb), MODE == 1 ? __int_as_float(P.types[n]) : r);
-                        sN[i] = n;
+                    for (int i = tid; i < nc; i += NT) {   // coalesced copy of the expanded entries
+                        const float4* src = reinterpret_cast<const float4*>(ent + r0 + i);
+                        float4 e0 = src[0], e1 = src[1];
+                        const float4 e2 = src[2];
+                        if (MODE == 2 && P.chan_radii != nullptr) {   // channel-wise features: this channel's radius
+                            const float r = P.chan_radii[c0];
+                            const float r2 = r * r;
+                            const float tau = r * P.tau_lin + r2 * P.tau_quad;
+                            const double rs = (double)r * P.sigma;
+                            e0.w = r2 + tau; e1.x = r2 - tau; e1.y = (float)(-0.5 * 1.4426950408889634 / (rs * rs));
+                            e1.w = r;
+                        }
+                        sA[i] = e0; sB[i] = e1;
+                        sN[i] = (int)__float_as_uint(e2.x);
+                        const unsigned long long m64 = (unsigned long long)__float_as_uint(e2.y) |
+                                                       ((unsigned long long)__float_as_uint(e2.z) << 32);
+                        sM[i] = (uint32_t)(m64 >> mask_shift);
                     }
                     if (MODE == 2) {
                         for (int i = tid; i < nc * CH; i += NT) {
                             const int j = i / CH, c = i - j * CH;
-                            const int n = (int)list[r0 + j];
+                            const int n = (int)ent[r0 + j].n;
                             sF[j * FS + c] = (c0 + c < P.C) ? P.features[(size_t)n * P.C + c0 + c] : 0.f;
                         }
                     }
                     __syncthreads();
-                    // cell masks: lane = cell, one staged atom per warp iteration, exact sphere / voxel-centre-box
+                    // cell masks when the expand pass could not precompute them (> 64 cells per column or another
+                    // cell shape): lane = cell, one staged atom per warp iteration, exact sphere / voxel-centre-box
                     // test; the ballot IS the atom's 32-bit mask of cells its cutoff sphere reaches
-                    {
+                    if (!P.masks) {
                         const float4 box = sBox[lane];
                         for (int i = warp; i < nc; i += NW) {
                             const float4 A = sA[i];
@@ -658,8 +756,8 @@ __global__ void __launch_bounds__(NT, (CH <= 8 ? 3 : 2) * (256 / NT)) mvx_voxeli
                             const uint32_t m = __ballot_sync(0xffffffffu, in);
                             if (lane == 0) sM[i] = m;
                         }
+                        __syncthreads();
                     }
-                    __syncthreads();
                     staged_c0 = c0;
                 }
                 if (!cell_ok) continue;   // warp-uniform
@@ -714,7 +812,7 @@ __global__ void __launch_bounds__(NT, (CH <= 8 ? 3 : 2) * (256 / NT)) mvx_voxeli
                                 const uint32_t forb = __float_as_uint(Bv.z);
                                 const uint32_t tx = forb ^ lane_key;
                                 const bool row_off = (tx & 0xFFu) == 0u || (tx & 0xFF00u) == 0u;
-                                const int dzf = (int)(forb >> 16) - lzv;
+                                const int dzf = (int)(forb >> 16) - z;
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) off[k] = row_off || dzf == k;
                             }

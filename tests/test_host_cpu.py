@@ -39,8 +39,8 @@ def test_workspace_planning_is_host_only():
     need = ctypes.c_size_t(0)
     assert L.mvx_workspace_bytes(ctypes.byref(spec), ctypes.byref(b), ctypes.byref(need)) == 0
     # 40 B record + 4 B column range + 4 columns x 4 B list entries per atom, 8 B per (molecule, column) bin
-    assert need.value >= 100_000 * (40 + 4 + 16) + 2048 * 64 * 8
-    assert L.mvx_launches_per_call(ctypes.byref(spec), ctypes.byref(b)) == 3
+    assert need.value >= 100_000 * (40 + 4 + 16 + 4 * 48) + 2048 * 64 * 8
+    assert L.mvx_launches_per_call(ctypes.byref(spec), ctypes.byref(b)) == 4   # prep, bin, expand, voxelize
 
 
 @pytest.mark.parametrize("mutate, code", [
