@@ -48,8 +48,10 @@ struct Plan {
     int ncol, nzc, tz, maxcols, nv;
     float tau_lin, tau_quad;
     // workspace offsets (bytes)
-    size_t off_status, off_recs, off_colrange, off_bins, off_lists, off_entries, total;
+    size_t off_status, off_recs, off_colrange, off_bins, off_lists, off_entries, off_cidx, off_cbins, total;
     int masks;   // expand pass precomputes the cell masks (<= 64 cells per column)
+    int use_lists;   // dense batch: expand also builds per-cell lists and the cell-list voxelize kernel runs
+    int cpe, ncell;
 };
 
 int check_args(const mvx_grid_spec* s, const mvx_batch* b) {
@@ -155,24 +157,45 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     pl->off_bins = off;     off += align_up(B * (size_t)pl->ncol * sizeof(uint2));
     pl->off_lists = off;    off += align_up(N * (size_t)pl->maxcols * sizeof(uint32_t));
     pl->off_entries = off;  off += align_up(pl->nv == 4 ? N * (size_t)pl->maxcols * sizeof(mvx::ColEntry) : 0);
-    pl->masks = pl->nzc * ((tz + mvx::kCellZ - 1) / mvx::kCellZ) * mvx::kCellsXY <= 64;
+    const int layers = pl->nzc * ((tz + mvx::kCellZ - 1) / mvx::kCellZ);
+    pl->ncell = layers * mvx::kCellsXY;
+    pl->masks = pl->nv == 4 && pl->ncell <= 64;
+    int zl = (int)std::floor(2.0 * reach * (1.0 + 1e-6) / (mvx::kCellZ * s->resolution)) + 2;   // z layers one sphere can reach
+    if (zl > layers) zl = layers;
+    pl->cpe = zl * mvx::kCellsXY;
+    // Kernel form by density.  Columns of a ligand batch hold a handful of atoms: CTA-staged "cells" kernel.
+    // Columns of a packed complex hold hundreds: the per-cell lists pay for themselves ("lists" kernel).
+    // Expected entries per column = atoms * columns-per-atom / columns; both forms give identical results.
+    {
+        const double cols_per_atom = std::pow(2.0 * reach / (mvx::kTile * s->resolution) + 1.0, 2.0);
+        const double per_col = (B > 0) ? (double)N * cols_per_atom / ((double)B * pl->ncol) : 0.0;
+        pl->use_lists = pl->masks && per_col >= 200.0;
+        if (const char* e = std::getenv("MVX_KERNEL")) {
+            if (std::strcmp(e, "lists") == 0) pl->use_lists = pl->masks;
+            else pl->use_lists = 0;
+        }
+    }
+    pl->off_cidx = off;     off += align_up(pl->use_lists ? N * (size_t)pl->maxcols * (size_t)pl->cpe * sizeof(uint32_t) : 0);
+    pl->off_cbins = off;    off += align_up(pl->use_lists ? B * (size_t)pl->ncol * (size_t)pl->ncell * sizeof(uint2) : 0);
     pl->total = off;
     return MVX_OK;
 }
 
 // kernel selection: "cells" (warp-cell form, D % 4 == 0) is the main path; "rows" is the generic form
 // (any D, scalar stores).  MVX_KERNEL=rows|cells and MVX_LPR=2|4|16 override for experiments.
-struct KernelChoice { bool cells; int lpr; };
+struct KernelChoice { bool cells; int lpr; bool lists; };
 
 KernelChoice choose_kernel(int nv) {
-    KernelChoice k{nv == 4, 4};
+    KernelChoice k{nv == 4, 4, nv == 4};
     if (const char* e = std::getenv("MVX_KERNEL")) {
-        if (std::strcmp(e, "rows") == 0) k.cells = false;
+        if (std::strcmp(e, "rows") == 0) { k.cells = false; k.lists = false; }
+        if (std::strcmp(e, "cells") == 0) k.lists = false;
     }
     if (const char* e = std::getenv("MVX_LPR")) {
         int v = std::atoi(e);
         if (v == 2 || v == 4 || v == 16) k.lpr = v;
     }
+    if (k.lpr != 4) k.lists = false;   // the cell lists are built for the 2 x 4 x 16 cell
     return k;
 }
 
@@ -198,7 +221,22 @@ cudaError_t launch_cells(const mvx::VoxParams& vp, unsigned grid, cudaStream_t s
 }
 
 template <int MODE, int CH, bool BINARY>
+cudaError_t launch_lists(const mvx::VoxParams& vp, unsigned grid, cudaStream_t st) {
+    constexpr size_t smem = mvx::lists_smem_bytes<MODE, CH>();
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(mvx::mvx_voxelize_lists_kernel<MODE, CH, BINARY>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    mvx::mvx_voxelize_lists_kernel<MODE, CH, BINARY><<<grid, mvx::kThreads, smem, st>>>(vp);
+    return cudaGetLastError();
+}
+
+template <int MODE, int CH, bool BINARY>
 cudaError_t launch_vox_nv(const mvx::VoxParams& vp, int nv, KernelChoice kc, unsigned grid, cudaStream_t st) {
+    if (kc.lists && nv == 4 && vp.masks && vp.use_lists) return launch_lists<MODE, CH, BINARY>(vp, grid, st);
     if (kc.cells && nv == 4) {
         if (kc.lpr == 4) return launch_cells<MODE, CH, BINARY, 4>(vp, grid, st);
         return launch_cells<MODE, CH, BINARY, 2>(vp, grid, st);  // MVX_LPR=2
@@ -345,6 +383,8 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, 
             ep.maxcols = pl.maxcols; ep.mode = batch->mode; ep.masks = pl.masks && kchoice.lpr == 4; ep.B = B;
             ep.mol_offsets = batch->mol_offsets; ep.recs = recs; ep.bins = bins; ep.lists = lists;
             ep.types = batch->types; ep.entries = entries;
+            ep.cpe = pl.cpe; ep.ncell = pl.ncell; ep.build_lists = pl.use_lists;
+            ep.cidx = (uint32_t*)(ws + pl.off_cidx); ep.cbins = (uint2*)(ws + pl.off_cbins);
             const long long warps = (long long)B * pl.ncol;
             mvx::mvx_expand_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(ep);
             MVX_CUDA_OK(cudaGetLastError());
@@ -360,6 +400,8 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, 
         vp.mol_offsets = batch->mol_offsets; vp.recs = recs; vp.bins = bins; vp.lists = lists;
         vp.types = batch->types; vp.features = batch->features; vp.chan_radii = nullptr; vp.out = out;
         vp.entries = entries; vp.masks = pl.masks && kchoice.lpr == 4;
+        vp.cpe = pl.cpe; vp.ncell = pl.ncell; vp.use_lists = pl.use_lists;
+        vp.cidx = (const uint32_t*)(ws + pl.off_cidx); vp.cbins = (const uint2*)(ws + pl.off_cbins);
         const unsigned long long nblk = (unsigned long long)B * pl.ncol * pl.nzc;
         if (nblk > 0x7fffffffULL) return fail(MVX_ERR_BAD_SHAPE, "batch too large for one launch; split it");
         const bool binary = spec->density_type == MVX_DENSITY_BINARY;

@@ -88,12 +88,18 @@ struct ExpandParams {
     double res, half_width, sigma;
     float tau_lin, tau_quad;
     int dim, ncx, ncol, nzc, tz, maxcols, mode, masks, B;
+    int build_lists;    // also build the per-cell lists (cell-list voxelize kernel)
     const int32_t* mol_offsets;
     const AtomRec* recs;
     const uint2* bins;
     const uint32_t* lists;
     const int32_t* types;
     ColEntry* entries;
+    // per-cell candidate lists (built when masks != 0): global entry indices, ascending, per (molecule, column, cell)
+    int cpe;            // capacity: cells one entry can reach
+    int ncell;          // cells per column = nzc * ceil(tz / 16) * 8  (<= 64)
+    uint32_t* cidx;     // column with entries [e0, e0 + cnt) owns cidx[e0 * cpe, (e0 + cnt) * cpe)
+    uint2* cbins;       // (start relative to the column's cidx segment, count) per (molecule, column, cell)
 };
 
 struct VoxParams {
@@ -112,6 +118,9 @@ struct VoxParams {
     const float* chan_radii;   // channel-wise features: kernel radius of channel c_begin
     const ColEntry* entries;   // expanded column lists (warp-cell kernel)
     int masks;                 // 1: entries carry precomputed cell masks
+    int cpe, ncell, use_lists; // per-cell lists (see ExpandParams)
+    const uint32_t* cidx;
+    const uint2* cbins;
     float* out;
 };
 
@@ -338,8 +347,11 @@ __global__ void mvx_bin_fill_kernel(const BinParams P, int groups) {
 // coefficient, packed forbidden planes, and the mask of warp cells the cutoff sphere reaches), so that the
 // voxelize kernel stages a column with one coalesced copy and no per-atom arithmetic.
 // ---------------------------------------------------------------------------------------------
+constexpr int kExpandSmemMasks = 512;   // masks of the first 512 entries of a column stay in shared memory
+
 __global__ void __launch_bounds__(256) mvx_expand_kernel(const ExpandParams P) {
-    const int lane = threadIdx.x & 31;
+    __shared__ unsigned long long s_mask[8 * kExpandSmemMasks];   // 32 KB
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (gw >= (long long)P.B * P.ncol) return;
     const int mol = (int)(gw / P.ncol), col = (int)(gw % P.ncol);
@@ -400,6 +412,54 @@ __global__ void __launch_bounds__(256) mvx_expand_kernel(const ExpandParams P) {
         float4* dst = reinterpret_cast<float4*>(P.entries + base + i);
         const float4* src = reinterpret_cast<const float4*>(&e);
         dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+        if (i < (uint32_t)kExpandSmemMasks) s_mask[warp * kExpandSmemMasks + i] = mask;
+    }
+    if (!P.masks || !P.build_lists) return;
+    // per-cell lists: for every cell of the column, the entries whose mask names it (order kept).
+    // pass 1 counts (lane = cell for the final prefix), pass 2 fills.
+    __syncwarp();
+    const unsigned long long* wm = s_mask + warp * kExpandSmemMasks;
+    auto mask_of = [&](uint32_t i) -> unsigned long long {
+        if (i < (uint32_t)kExpandSmemMasks) return wm[i];
+        const ColEntry* e = P.entries + base + i;   // rare: very long column lists re-read their masks
+        return (unsigned long long)e->mask_lo | ((unsigned long long)e->mask_hi << 32);
+    };
+    // counts: each lane accumulates popcounts per cell for its entries, then a warp reduction per cell
+    uint32_t my_cnt_lo = 0, my_cnt_hi = 0;   // lane c holds the count of cell c (lo: cells 0-31, hi: 32-63)
+    for (int c = 0; c < P.ncell; ++c) {
+        uint32_t cnt = 0;
+        for (uint32_t i0 = 0; i0 < bin.y; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const bool in = i < bin.y && ((mask_of(i) >> c) & 1ull);
+            cnt += __popc(__ballot_sync(0xffffffffu, in));
+        }
+        if ((c & 31) == lane) { if (c < 32) my_cnt_lo = cnt; else my_cnt_hi = cnt; }
+    }
+    // exclusive prefix over the cells (two 32-wide scans)
+    uint32_t x = my_cnt_lo;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    const uint32_t off_lo = x - my_cnt_lo;
+    const uint32_t total_lo = __shfl_sync(0xffffffffu, x, 31);
+    x = my_cnt_hi;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    const uint32_t off_hi = total_lo + x - my_cnt_hi;
+    uint2* cb = P.cbins + (size_t)gw * P.ncell;
+    if (lane < P.ncell) cb[lane] = make_uint2(off_lo, my_cnt_lo);
+    if (lane + 32 < P.ncell) cb[lane + 32] = make_uint2(off_hi, my_cnt_hi);
+    uint32_t* seg = P.cidx + base * (size_t)P.cpe;
+    for (int c = 0; c < P.ncell; ++c) {
+        uint32_t pos = __shfl_sync(0xffffffffu, c < 32 ? off_lo : off_hi, c & 31);
+        const uint32_t n_c = __shfl_sync(0xffffffffu, c < 32 ? my_cnt_lo : my_cnt_hi, c & 31);
+        if (n_c == 0) continue;
+        for (uint32_t i0 = 0; i0 < bin.y; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const bool in = i < bin.y && ((mask_of(i) >> c) & 1ull);
+            const uint32_t m = __ballot_sync(0xffffffffu, in);
+            if (in) seg[pos + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(base + i);
+            pos += __popc(m);
+        }
     }
 }
 
@@ -865,6 +925,229 @@ __global__ void __launch_bounds__(NT, (CH <= 8 ? 3 : 2) * (256 / NT)) mvx_voxeli
                     }
                     __syncwarp();
                 }
+            }
+            if (valid) {
+                float* p = out_mol + (size_t)c0 * plane + ((size_t)x * D + y) * D + z;
+                if (c0 + CH <= P.c_end) {
+#pragma unroll
+                    for (int c = 0; c < CH; ++c, p += plane) store_vox(p, acc[c]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CH; ++c, p += plane)
+                        if (c0 + c < P.c_end) store_vox(p, acc[c]);
+                }
+            }
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// voxelize, "cell-list" form (the fast path: D % 4 == 0 and <= 64 cells per column).  The expand pass has
+// already built, per (molecule, column, cell), the ordered list of entries whose cutoff sphere reaches the
+// cell, so warps are fully independent here: no CTA-wide staging, no barriers.  A warp owns a cell of
+// 2 x 4 x 16 voxels (lane = 4 voxels along z): it copies the cell's entries (and feature rows) into its
+// private shared-memory slice, tests them against its voxels (bitmask per lane) and then each lane walks
+// its own hits in ascending order, accumulating CH channels in registers; one 128-bit store per channel.
+// ---------------------------------------------------------------------------------------------
+template <int MODE, int CH>
+constexpr size_t lists_smem_bytes() {
+    return (size_t)(kThreads / 32) * kWarpList * (2 * sizeof(float4) + sizeof(int) + (MODE == 2 ? feat_stride<CH>() * sizeof(float) : 0));
+}
+
+template <int MODE, int CH, bool BINARY>
+__global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_lists_kernel(const VoxParams P) {
+    constexpr int LPR = 4, RX = kCellX, RY = kCellY, CZ = kCellZ;
+    constexpr int NCY = kTile / RY;
+    constexpr int NW = kThreads / 32;
+    constexpr int FS = feat_stride<CH>();
+    constexpr int WBYTES = kWarpList * (2 * sizeof(float4) + sizeof(int) + (MODE == 2 ? FS * sizeof(float) : 0));
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float4* wA = reinterpret_cast<float4*>(smem_raw + (size_t)warp * WBYTES);
+    float4* wB = wA + kWarpList;
+    int* wN = reinterpret_cast<int*>(wB + kWarpList);
+    float* wF = reinterpret_cast<float*>(wN + kWarpList);
+
+    int t = blockIdx.x;
+    const int zc = t % P.nzc; t /= P.nzc;
+    const int col = t % P.ncol;
+    const int mol = t / P.ncol;
+    const int x0 = (col / P.ncx) * kTile, y0 = (col % P.ncx) * kTile, z0 = zc * P.tz;
+    const int D = P.dim;
+    const int z1 = min(D, z0 + P.tz);
+    const size_t plane = (size_t)D * D * D;
+    float* out_mol = P.out + (size_t)mol * P.Cout * plane;
+
+    const uint2 bin = P.bins[(size_t)mol * P.ncol + col];
+
+    if (bin.y == 0) {   // empty column: pure zero fill, one address computation per thread item
+        const int lz = (z1 - z0) >> 2;
+        const int nitems = kTile * kTile * lz;
+        const int qstep = kThreads / lz, rstep = kThreads - qstep * lz;
+        int row = tid / lz, lzi = tid - row * lz;
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int item = tid; item < nitems; item += kThreads) {
+            const int x = x0 + (row >> 3), y = y0 + (row & 7);
+            if (x < D && y < D) {
+                float* p = out_mol + (size_t)P.c_begin * plane + ((size_t)x * D + y) * D + z0 + lzi * 4;
+                for (int ch = P.c_begin; ch < P.c_end; ++ch, p += plane) __stcs(reinterpret_cast<float4*>(p), zero);
+            }
+            row += qstep; lzi += rstep;
+            if (lzi >= lz) { lzi -= lz; ++row; }
+        }
+        return;
+    }
+
+    const int ncz_max = (P.tz + CZ - 1) / CZ;
+    const uint2* cb = P.cbins + ((size_t)mol * P.ncol + col) * P.ncell + (size_t)zc * ncz_max * kCellsXY;
+    const uint32_t* seg = P.cidx + ((size_t)P.mol_offsets[mol] * (size_t)P.maxcols + bin.x) * (size_t)P.cpe;
+    const float resf = (float)P.res;
+    const float inv_res = 1.0f / resf;
+    const int row = lane / LPR, zq = lane % LPR;
+    const int rx = row / RY, ry = row % RY;
+    const int ncz = (z1 - z0 + CZ - 1) / CZ;
+    const int ncells = kCellsXY * ncz;
+    const bool vec_feat = (P.C % 4) == 0;
+
+    for (int c0 = P.c_begin; c0 < P.c_end; c0 += CH) {
+        for (int cell = warp; cell < ncells; cell += NW) {
+            const int cz = cell / kCellsXY, cxy = cell % kCellsXY;
+            const int cxl = cxy / NCY, cyl = cxy % NCY;
+            const int lx = cxl * RX + rx, ly = cyl * RY + ry, lzv = cz * CZ + zq * 4;
+            const int x = x0 + lx, y = y0 + ly, z = z0 + lzv;
+            const bool valid = x < D && y < D && z < z1;
+            const uint32_t lane_key = (uint32_t)lx | ((uint32_t)ly << 8);
+            const float ox = (float)((double)lx * P.res), oy = (float)((double)ly * P.res);
+            float oz[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) oz[k] = (float)((double)(z + k) * P.res);   // grid-absolute, like ColEntry::az
+
+            float acc[CH][4];
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[c][k] = 0.f;
+
+            const uint2 cbin = cb[cell];
+            for (uint32_t j0 = 0; j0 < cbin.y; j0 += kWarpList) {
+                const int wn = (int)min((uint32_t)kWarpList, cbin.y - j0);
+                // 1. this warp's candidates: entries (and feature rows) -> warp-private shared memory
+                for (int jj = lane; jj < wn; jj += 32) {
+                    const float4* src = reinterpret_cast<const float4*>(P.entries + seg[cbin.x + j0 + jj]);
+                    float4 e0 = src[0], e1 = src[1];
+                    const int n = (int)__float_as_uint(src[2].x);
+                    if (MODE == 2 && P.chan_radii != nullptr) {   // channel-wise features: this channel's radius
+                        const float r = P.chan_radii[c0];
+                        const float r2 = r * r;
+                        const float tau = r * P.tau_lin + r2 * P.tau_quad;
+                        const double rs = (double)r * P.sigma;
+                        e0.w = r2 + tau; e1.x = r2 - tau; e1.y = (float)(-0.5 * 1.4426950408889634 / (rs * rs));
+                        e1.w = r;
+                    }
+                    wA[jj] = e0; wB[jj] = e1; wN[jj] = n;
+                    if (MODE == 2) {
+                        const float* f = P.features + (size_t)n * P.C + c0;
+                        float* d = wF + jj * FS;
+                        if (vec_feat && CH >= 4) {
+#pragma unroll
+                            for (int c4 = 0; c4 < CH; c4 += 4)
+                                *reinterpret_cast<float4*>(d + c4) =
+                                    (c0 + c4 < P.C) ? __ldg(reinterpret_cast<const float4*>(f + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < CH; ++c) d[c] = (c0 + c < P.C) ? __ldg(f + c) : 0.f;
+                        }
+                    }
+                }
+                __syncwarp();
+                // 2. every lane tests the list against the nearest of its 4 voxels; candidate hits -> bitmasks
+                uint32_t mask_lo = 0u, mask_hi = 0u;
+                if (valid) {
+                    auto near_hit = [&](const float4 A) -> bool {
+                        const float dx = A.x - ox, dy = A.y - oy;
+                        const float tz_ = A.z - oz[0];
+                        const float dzc = fmaf(-resf, fminf(fmaxf(rintf(tz_ * inv_res), 0.f), 3.f), tz_);
+                        return fmaf(dzc, dzc, fmaf(dx, dx, dy * dy)) <= A.w;
+                    };
+                    const int n_lo = min(wn, 32);
+#pragma unroll 4
+                    for (int j = 0; j < n_lo; ++j)
+                        if (near_hit(wA[j])) mask_lo |= 1u << j;
+#pragma unroll 4
+                    for (int j = 32; j < wn; ++j)
+                        if (near_hit(wA[j])) mask_hi |= 1u << (j - 32);
+                }
+                // 3. lane-private walk over the set bits, ascending (fixed fp32 summation order)
+                while (__any_sync(0xffffffffu, (mask_lo | mask_hi) != 0u)) {
+                    if ((mask_lo | mask_hi) != 0u) {
+                        int j;
+                        if (mask_lo != 0u) { j = __ffs((int)mask_lo) - 1; mask_lo &= mask_lo - 1u; }
+                        else { j = 31 + __ffs((int)mask_hi); mask_hi &= mask_hi - 1u; }
+                        const float4 A = wA[j];
+                        const float4 Bv = wB[j];
+                        const float dx = A.x - ox, dy = A.y - oy;
+                        const float dxy = fmaf(dx, dx, dy * dy);
+                        bool off[4] = {false, false, false, false};
+                        if (P.cull) {   // uniform: block-cull emulation, voxels on the atom's forbidden planes take nothing
+                            const uint32_t forb = __float_as_uint(Bv.z);
+                            const uint32_t tx = forb ^ lane_key;
+                            const bool row_off = (tx & 0xFFu) == 0u || (tx & 0xFF00u) == 0u;
+                            const int dzf = (int)(forb >> 16) - z;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) off[k] = row_off || dzf == k;
+                        }
+                        // band centre / half width: |s - r^2| <= tau decides "replay in fp64"
+                        const float r2c = 0.5f * (A.w + Bv.x), tauh = 0.5f * (A.w - Bv.x) * 1.0001f + 1e-12f;
+                        float sk[4], w[4], dmin = 3.0e38f;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float dz = A.z - oz[k];
+                            sk[k] = fmaf(dz, dz, dxy);
+                            w[k] = (sk[k] < Bv.x && !off[k]) ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
+                            dmin = fminf(dmin, fabsf(sk[k] - r2c));
+                        }
+                        if (dmin <= tauh) {   // rare: voxels inside the tolerance band replay the reference's fp64 arithmetic
+                            const int n = wN[j];
+                            const float r32 = (MODE == 1) ? P.recs[n].r : Bv.w;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (sk[k] >= Bv.x && !off[k]) {
+                                    const bool hit = sk[k] <= A.w && exact_hit(P.recs + n, r32, x, y, z + k, P.res, P.half_width);
+                                    w[k] = hit ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
+                                }
+                            }
+                        }
+                        if (MODE == 0) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) acc[0][k] += w[k];
+                        } else if (MODE == 1) {
+                            const int ct = __float_as_int(Bv.w) - c0;
+#pragma unroll
+                            for (int c = 0; c < CH; ++c)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) acc[c][k] += (ct == c) ? w[k] : 0.f;
+                        } else {
+                            const float* frow = wF + j * FS;
+#pragma unroll
+                            for (int c4 = 0; c4 < CH; c4 += 4) {
+                                float f[4];
+                                if (CH >= 4) {
+                                    const float4 fv = *reinterpret_cast<const float4*>(frow + c4);
+                                    f[0] = fv.x; f[1] = fv.y; f[2] = fv.z; f[3] = fv.w;
+                                } else {
+                                    f[0] = frow[0]; f[1] = f[2] = f[3] = 0.f;
+                                }
+#pragma unroll
+                                for (int cc = 0; cc < 4 && c4 + cc < CH; ++cc)
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) acc[c4 + cc][k] = fmaf(f[cc], w[k], acc[c4 + cc][k]);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
             }
             if (valid) {
                 float* p = out_mol + (size_t)c0 * plane + ((size_t)x * D + y) * D + z;
