@@ -408,7 +408,7 @@ def run_b200_arm(args):
                      "traffic": traffic, "kernel": "mvx_voxelize_kernel", "kernel_ms": prof["vox"],
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "write_only_reference_gbs": fill_gbs,
-                     "note": "peak is the measured COPY bandwidth (read+write); this kernel only writes, so frac can exceed 1.0 — write_only_reference_gbs is torch's fill kernel on the same buffers",
+                     "note": "peak is the measured COPY bandwidth (read+write); this kernel only writes, so frac can exceed 1.0 — write_only_reference_gbs is torch zero_() (device memset) on the same buffers",
                      "step_share": {"prep_ms": prof["prep"], "bin_ms": prof["bin"], "voxelize_ms": prof["vox"]}},
         "clocks": clocks,
     }
