@@ -48,10 +48,12 @@ struct Plan {
     int ncol, nzc, tz, maxcols, nv;
     float tau_lin, tau_quad;
     // workspace offsets (bytes)
-    size_t off_status, off_recs, off_colrange, off_bins, off_lists, off_entries, off_cidx, off_cbins, total;
+    size_t off_status, off_recs, off_colrange, off_bins, off_lists, off_entries, total;
     int masks;   // expand pass precomputes the cell masks (<= 64 cells per column)
-    int use_lists;   // dense batch: expand also builds per-cell lists and the cell-list voxelize kernel runs
-    int cpe, ncell;
+    int form;        // voxelize kernel form, see enum Form
+    int ncell;
+    int nlayers, zl, es4;
+    size_t off_lent, off_lmask, off_lbins;
 };
 
 int check_args(const mvx_grid_spec* s, const mvx_batch* b) {
@@ -87,6 +89,15 @@ int check_args(const mvx_grid_spec* s, const mvx_batch* b) {
     }
     return MVX_OK;
 }
+
+int pick_chunk(int mode, int nchan);
+
+// Voxelize kernel forms.  All give identical results; they differ in how a tile's atoms reach the warps.
+//   CELLS  column entries (48 B) with cell masks, features gathered at staging: sparse / medium batches
+//   TILES  entries regrouped per 16-voxel z layer with their feature rows, one flat staging copy,
+//          per-layer warp filter: packed complexes (hundreds of atoms per column)
+//   ROWS   generic lock-step form (any D, scalar stores when D % 4 != 0)
+enum Form { FORM_ROWS = 0, FORM_CELLS = 1, FORM_TILES = 3 };
 
 int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     int rc = check_args(s, b);
@@ -156,99 +167,80 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     pl->off_colrange = off; off += align_up(N * sizeof(uint32_t));
     pl->off_bins = off;     off += align_up(B * (size_t)pl->ncol * sizeof(uint2));
     pl->off_lists = off;    off += align_up(N * (size_t)pl->maxcols * sizeof(uint32_t));
-    pl->off_entries = off;  off += align_up(pl->nv == 4 ? N * (size_t)pl->maxcols * sizeof(mvx::ColEntry) : 0);
     const int layers = pl->nzc * ((tz + mvx::kCellZ - 1) / mvx::kCellZ);
     pl->ncell = layers * mvx::kCellsXY;
     pl->masks = pl->nv == 4 && pl->ncell <= 64;
     int zl = (int)std::floor(2.0 * reach * (1.0 + 1e-6) / (mvx::kCellZ * s->resolution)) + 2;   // z layers one sphere can reach
     if (zl > layers) zl = layers;
-    pl->cpe = zl * mvx::kCellsXY;
-    // Kernel form by density.  Columns of a ligand batch hold a handful of atoms: CTA-staged "cells" kernel.
-    // Columns of a packed complex hold hundreds: the per-cell lists pay for themselves ("lists" kernel).
-    // Expected entries per column = atoms * columns-per-atom / columns; both forms give identical results.
+    // Kernel form by density: expected entries per column = atoms * columns-per-atom / columns.
     {
         const double cols_per_atom = std::pow(2.0 * reach / (mvx::kTile * s->resolution) + 1.0, 2.0);
         const double per_col = (B > 0) ? (double)N * cols_per_atom / ((double)B * pl->ncol) : 0.0;
-        pl->use_lists = pl->masks && per_col >= 200.0;
-        if (const char* e = std::getenv("MVX_KERNEL")) {
-            if (std::strcmp(e, "lists") == 0) pl->use_lists = pl->masks;
-            else pl->use_lists = 0;
+        pl->form = pl->nv != 4 ? FORM_ROWS : (per_col >= 200.0 ? FORM_TILES : FORM_CELLS);
+        if (const char* e = std::getenv("MVX_KERNEL")) {   // experiments / tests
+            if (std::strcmp(e, "rows") == 0) pl->form = FORM_ROWS;
+            else if (pl->nv == 4 && std::strcmp(e, "cells") == 0) pl->form = FORM_CELLS;
+            else if (pl->nv == 4 && std::strcmp(e, "tiles") == 0) pl->form = FORM_TILES;
         }
     }
-    pl->off_cidx = off;     off += align_up(pl->use_lists ? N * (size_t)pl->maxcols * (size_t)pl->cpe * sizeof(uint32_t) : 0);
-    pl->off_cbins = off;    off += align_up(pl->use_lists ? B * (size_t)pl->ncol * (size_t)pl->ncell * sizeof(uint2) : 0);
+    {   // layered entries of the tile kernel
+        const int C = b->mode == MVX_MODE_FEATURES ? b->num_channels : 0;
+        int chunk = pick_chunk(b->mode, b->out_channels);
+        if (chunk < 4) chunk = 4;
+        const int cs = (C + chunk - 1) / chunk * chunk;
+        pl->es4 = 3 + cs / 4;
+        pl->nlayers = layers;
+        pl->zl = zl;
+        const size_t nle = pl->form == FORM_TILES ? N * (size_t)pl->maxcols * (size_t)zl : 0;
+        pl->off_lent = off;  off += align_up(nle * (size_t)pl->es4 * 16);
+        pl->off_lmask = off; off += align_up(nle * sizeof(uint32_t));
+        pl->off_lbins = off; off += align_up(pl->form == FORM_TILES ? B * (size_t)pl->ncol * (size_t)layers * sizeof(uint2) : 0);
+    }
+    pl->off_entries = off;  off += align_up(pl->form == FORM_CELLS ? N * (size_t)pl->maxcols * sizeof(mvx::ColEntry) : 0);
     pl->total = off;
     return MVX_OK;
 }
 
-// kernel selection: "cells" (warp-cell form, D % 4 == 0) is the main path; "rows" is the generic form
-// (any D, scalar stores).  MVX_KERNEL=rows|cells and MVX_LPR=2|4|16 override for experiments.
-struct KernelChoice { bool cells; int lpr; bool lists; };
-
-KernelChoice choose_kernel(int nv) {
-    KernelChoice k{nv == 4, 4, nv == 4};
-    if (const char* e = std::getenv("MVX_KERNEL")) {
-        if (std::strcmp(e, "rows") == 0) { k.cells = false; k.lists = false; }
-        if (std::strcmp(e, "cells") == 0) k.lists = false;
-    }
-    if (const char* e = std::getenv("MVX_LPR")) {
-        int v = std::atoi(e);
-        if (v == 2 || v == 4 || v == 16) k.lpr = v;
-    }
-    if (k.lpr != 4) k.lists = false;   // the cell lists are built for the 2 x 4 x 16 cell
-    return k;
+int env_lpr() {   // MVX_LPR=2|4: cell shape of the legacy CELLS form (experiments)
+    if (const char* e = std::getenv("MVX_LPR")) { int v = std::atoi(e); if (v == 2 || v == 4) return v; }
+    return 4;
 }
 
-template <int MODE, int CH, bool BINARY, int LPR, int NT>
-cudaError_t launch_cells_nt(const mvx::VoxParams& vp, unsigned grid, cudaStream_t st) {
-    constexpr size_t smem = mvx::cells_smem_bytes<MODE, CH, NT>();
-    static bool configured = false;   // per instantiation; benign race (idempotent attribute)
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, LPR, NT>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, LPR, NT><<<grid, NT, smem, st>>>(vp);
-    return cudaGetLastError();
-}
-
-template <int MODE, int CH, bool BINARY, int LPR>
-cudaError_t launch_cells(const mvx::VoxParams& vp, unsigned grid, cudaStream_t st) {
-    static const int nt = [] { const char* e = std::getenv("MVX_NT"); return e ? std::atoi(e) : 256; }();
-    if (nt == 128) return launch_cells_nt<MODE, CH, BINARY, LPR, 128>(vp, grid, st);
-    return launch_cells_nt<MODE, CH, BINARY, LPR, 256>(vp, grid, st);
+template <typename K>
+cudaError_t set_smem(K kernel, size_t smem) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 template <int MODE, int CH, bool BINARY>
-cudaError_t launch_lists(const mvx::VoxParams& vp, unsigned grid, cudaStream_t st) {
-    constexpr size_t smem = mvx::lists_smem_bytes<MODE, CH>();
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(mvx::mvx_voxelize_lists_kernel<MODE, CH, BINARY>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
+cudaError_t launch_form(const mvx::VoxParams& vp, int form, int nv, unsigned grid, cudaStream_t st) {
+    if (form == FORM_TILES) {
+        constexpr size_t smem = mvx::tiles_smem_bytes<MODE>();
+        static bool cfg = false;
+        if (!cfg) { cudaError_t e = set_smem(mvx::mvx_voxelize_tiles_kernel<MODE, CH, BINARY>, smem); if (e != cudaSuccess) return e; cfg = true; }
+        mvx::mvx_voxelize_tiles_kernel<MODE, CH, BINARY><<<grid, mvx::kThreads, smem, st>>>(vp);
+    } else if (form == FORM_CELLS) {
+        if (env_lpr() == 2) {
+            constexpr size_t smem = mvx::cells_smem_bytes<MODE, CH, 256>();
+            static bool cfg = false;
+            if (!cfg) { cudaError_t e = set_smem(mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, 2, 256>, smem); if (e != cudaSuccess) return e; cfg = true; }
+            mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, 2, 256><<<grid, 256, smem, st>>>(vp);
+        } else {
+            constexpr size_t smem = mvx::cells_smem_bytes<MODE, CH, 256>();
+            static bool cfg = false;
+            if (!cfg) { cudaError_t e = set_smem(mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, 4, 256>, smem); if (e != cudaSuccess) return e; cfg = true; }
+            mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, 4, 256><<<grid, 256, smem, st>>>(vp);
+        }
+    } else if (nv == 4) {
+        mvx::mvx_voxelize_kernel<MODE, CH, BINARY, 4><<<grid, mvx::kThreads, 0, st>>>(vp);
+    } else {
+        mvx::mvx_voxelize_kernel<MODE, CH, BINARY, 1><<<grid, mvx::kThreads, 0, st>>>(vp);
     }
-    mvx::mvx_voxelize_lists_kernel<MODE, CH, BINARY><<<grid, mvx::kThreads, smem, st>>>(vp);
-    return cudaGetLastError();
-}
-
-template <int MODE, int CH, bool BINARY>
-cudaError_t launch_vox_nv(const mvx::VoxParams& vp, int nv, KernelChoice kc, unsigned grid, cudaStream_t st) {
-    if (kc.lists && nv == 4 && vp.masks && vp.use_lists) return launch_lists<MODE, CH, BINARY>(vp, grid, st);
-    if (kc.cells && nv == 4) {
-        if (kc.lpr == 4) return launch_cells<MODE, CH, BINARY, 4>(vp, grid, st);
-        return launch_cells<MODE, CH, BINARY, 2>(vp, grid, st);  // MVX_LPR=2
-    }
-    if (nv == 4) mvx::mvx_voxelize_kernel<MODE, CH, BINARY, 4><<<grid, mvx::kThreads, 0, st>>>(vp);
-    else mvx::mvx_voxelize_kernel<MODE, CH, BINARY, 1><<<grid, mvx::kThreads, 0, st>>>(vp);
     return cudaGetLastError();
 }
 
 template <int MODE, int CH>
-cudaError_t launch_vox_density(const mvx::VoxParams& vp, bool binary, int nv, KernelChoice kc, unsigned grid, cudaStream_t st) {
-    return binary ? launch_vox_nv<MODE, CH, true>(vp, nv, kc, grid, st) : launch_vox_nv<MODE, CH, false>(vp, nv, kc, grid, st);
+cudaError_t launch_density(const mvx::VoxParams& vp, bool binary, int form, int nv, unsigned grid, cudaStream_t st) {
+    return binary ? launch_form<MODE, CH, true>(vp, form, nv, grid, st) : launch_form<MODE, CH, false>(vp, form, nv, grid, st);
 }
 
 // column groups per molecule for the bin pass: 1 (fused kernel) once the batch alone gives two waves of
@@ -273,22 +265,21 @@ int pick_chunk(int mode, int nchan) {
     return 16;
 }
 
-cudaError_t launch_vox(int mode, int ch, const mvx::VoxParams& vp, bool binary, int nv, unsigned grid, cudaStream_t st) {
-    const KernelChoice kc = choose_kernel(nv);
-    if (mode == MVX_MODE_SINGLE) return launch_vox_density<0, 1>(vp, binary, nv, kc, grid, st);
+cudaError_t launch_vox(int mode, int ch, const mvx::VoxParams& vp, bool binary, int form, int nv, unsigned grid, cudaStream_t st) {
+    if (mode == MVX_MODE_SINGLE) return launch_density<0, 1>(vp, binary, form, nv, grid, st);
     if (mode == MVX_MODE_TYPES) {
         switch (ch) {
-            case 1: return launch_vox_density<1, 1>(vp, binary, nv, kc, grid, st);
-            case 4: return launch_vox_density<1, 4>(vp, binary, nv, kc, grid, st);
-            case 8: return launch_vox_density<1, 8>(vp, binary, nv, kc, grid, st);
-            default: return launch_vox_density<1, 16>(vp, binary, nv, kc, grid, st);
+            case 1: return launch_density<1, 1>(vp, binary, form, nv, grid, st);
+            case 4: return launch_density<1, 4>(vp, binary, form, nv, grid, st);
+            case 8: return launch_density<1, 8>(vp, binary, form, nv, grid, st);
+            default: return launch_density<1, 16>(vp, binary, form, nv, grid, st);
         }
     }
     switch (ch) {
-        case 1: return launch_vox_density<2, 1>(vp, binary, nv, kc, grid, st);
-        case 4: return launch_vox_density<2, 4>(vp, binary, nv, kc, grid, st);
-        case 8: return launch_vox_density<2, 8>(vp, binary, nv, kc, grid, st);
-        default: return launch_vox_density<2, 16>(vp, binary, nv, kc, grid, st);
+        case 1: return launch_density<2, 1>(vp, binary, form, nv, grid, st);
+        case 4: return launch_density<2, 4>(vp, binary, form, nv, grid, st);
+        case 8: return launch_density<2, 8>(vp, binary, form, nv, grid, st);
+        default: return launch_density<2, 16>(vp, binary, form, nv, grid, st);
     }
 }
 
@@ -317,7 +308,7 @@ int mvx_launches_per_call(const mvx_grid_spec* spec, const mvx_batch* batch) {
     const bool chan_feat = batch->mode == MVX_MODE_FEATURES && spec->radii_type == MVX_RADII_CHANNEL_WISE;
     int nvox = chan_feat ? batch->num_channels : 1;
     const int nbin = bin_groups(batch->num_mols, pl.ncol) <= 1 ? 1 : 2;
-    const int nexp = (choose_kernel(pl.nv).cells && batch->total_atoms > 0) ? 1 : 0;
+    const int nexp = (pl.form != FORM_ROWS && batch->total_atoms > 0) ? 1 : 0;
     return (batch->total_atoms > 0 ? 1 : 0) + nbin + nexp + nvox;   // prep + bin + expand + voxelize
 }
 
@@ -339,7 +330,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, 
     uint2* bins = (uint2*)(ws + pl.off_bins);
     uint32_t* lists = (uint32_t*)(ws + pl.off_lists);
     mvx::ColEntry* entries = (mvx::ColEntry*)(ws + pl.off_entries);
-    const KernelChoice kchoice = choose_kernel(pl.nv);
+    const bool legacy_masks = pl.masks && env_lpr() == 4;   // CELLS form: masks precomputed by expand
 
     const int B = batch->num_mols;
     const int64_t N = batch->total_atoms;
@@ -375,18 +366,21 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, 
             mvx::mvx_bin_fill_kernel<<<(unsigned)(B * groups), 256, smem, st>>>(bp, groups);
         }
         MVX_CUDA_OK(cudaGetLastError());
-        if (kchoice.cells && N > 0) {   // column lists -> staged-ready entries for the warp-cell kernel
+        if (pl.form != FORM_ROWS && N > 0) {   // column lists -> staged-ready entries
             mvx::ExpandParams ep;
             ep.res = pl.geo.res; ep.half_width = pl.geo.half_width; ep.sigma = spec->sigma;
             ep.tau_lin = pl.tau_lin; ep.tau_quad = pl.tau_quad;
             ep.dim = spec->dimension; ep.ncx = pl.geo.ncx; ep.ncol = pl.ncol; ep.nzc = pl.nzc; ep.tz = pl.tz;
-            ep.maxcols = pl.maxcols; ep.mode = batch->mode; ep.masks = pl.masks && kchoice.lpr == 4; ep.B = B;
+            ep.maxcols = pl.maxcols; ep.mode = batch->mode; ep.masks = legacy_masks; ep.B = B;
             ep.mol_offsets = batch->mol_offsets; ep.recs = recs; ep.bins = bins; ep.lists = lists;
             ep.types = batch->types; ep.entries = entries;
-            ep.cpe = pl.cpe; ep.ncell = pl.ncell; ep.build_lists = pl.use_lists;
-            ep.cidx = (uint32_t*)(ws + pl.off_cidx); ep.cbins = (uint2*)(ws + pl.off_cbins);
+            ep.nlayers = pl.nlayers; ep.zl = pl.zl; ep.es4 = pl.es4;
+            ep.C = batch->mode == MVX_MODE_FEATURES ? C : 0; ep.features = batch->features;
+            ep.lent = (float4*)(ws + pl.off_lent); ep.lmask = (uint32_t*)(ws + pl.off_lmask);
+            ep.lbins = (uint2*)(ws + pl.off_lbins);
             const long long warps = (long long)B * pl.ncol;
-            mvx::mvx_expand_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(ep);
+            if (pl.form == FORM_TILES) mvx::mvx_expand_layers_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(ep);
+            else mvx::mvx_expand_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(ep);
             MVX_CUDA_OK(cudaGetLastError());
         }
     }
@@ -399,9 +393,10 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, 
         vp.C = C; vp.Cout = batch->out_channels; vp.maxcols = pl.maxcols; vp.cull = pl.geo.nb > 1;
         vp.mol_offsets = batch->mol_offsets; vp.recs = recs; vp.bins = bins; vp.lists = lists;
         vp.types = batch->types; vp.features = batch->features; vp.chan_radii = nullptr; vp.out = out;
-        vp.entries = entries; vp.masks = pl.masks && kchoice.lpr == 4;
-        vp.cpe = pl.cpe; vp.ncell = pl.ncell; vp.use_lists = pl.use_lists;
-        vp.cidx = (const uint32_t*)(ws + pl.off_cidx); vp.cbins = (const uint2*)(ws + pl.off_cbins);
+        vp.entries = entries; vp.masks = legacy_masks;
+        vp.nlayers = pl.nlayers; vp.zl = pl.zl; vp.es4 = pl.es4;
+        vp.lent = (const float4*)(ws + pl.off_lent); vp.lmask = (const uint32_t*)(ws + pl.off_lmask);
+        vp.lbins = (const uint2*)(ws + pl.off_lbins);
         const unsigned long long nblk = (unsigned long long)B * pl.ncol * pl.nzc;
         if (nblk > 0x7fffffffULL) return fail(MVX_ERR_BAD_SHAPE, "batch too large for one launch; split it");
         const bool binary = spec->density_type == MVX_DENSITY_BINARY;
@@ -409,11 +404,11 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, 
         if (chan_feat) {   // per-channel radius: one pass per channel (numpy/voxelizer.py:213-224)
             for (int c = 0; c < C; ++c) {
                 vp.c_begin = c; vp.c_end = c + 1; vp.chan_radii = batch->radii;
-                MVX_CUDA_OK(launch_vox(batch->mode, 1, vp, binary, pl.nv, (unsigned)nblk, st));
+                MVX_CUDA_OK(launch_vox(batch->mode, 1, vp, binary, pl.form, pl.nv, (unsigned)nblk, st));
             }
         } else {
             vp.c_begin = 0; vp.c_end = batch->out_channels;
-            MVX_CUDA_OK(launch_vox(batch->mode, pick_chunk(batch->mode, batch->out_channels), vp, binary, pl.nv,
+            MVX_CUDA_OK(launch_vox(batch->mode, pick_chunk(batch->mode, batch->out_channels), vp, binary, pl.form, pl.nv,
                                    (unsigned)nblk, st));
         }
     }

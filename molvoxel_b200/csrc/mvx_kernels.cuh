@@ -88,18 +88,21 @@ struct ExpandParams {
     double res, half_width, sigma;
     float tau_lin, tau_quad;
     int dim, ncx, ncol, nzc, tz, maxcols, mode, masks, B;
-    int build_lists;    // also build the per-cell lists (cell-list voxelize kernel)
     const int32_t* mol_offsets;
     const AtomRec* recs;
     const uint2* bins;
     const uint32_t* lists;
     const int32_t* types;
-    ColEntry* entries;
-    // per-cell candidate lists (built when masks != 0): global entry indices, ascending, per (molecule, column, cell)
-    int cpe;            // capacity: cells one entry can reach
-    int ncell;          // cells per column = nzc * ceil(tz / 16) * 8  (<= 64)
-    uint32_t* cidx;     // column with entries [e0, e0 + cnt) owns cidx[e0 * cpe, (e0 + cnt) * cpe)
-    uint2* cbins;       // (start relative to the column's cidx segment, count) per (molecule, column, cell)
+    ColEntry* entries;   // CELLS form: one 48-byte record per (column, atom)
+    // TILES form: entries regrouped per 16-voxel z layer, feature rows appended
+    int nlayers;        // nzc * ceil(tz / 16)  (<= 32)
+    int zl;             // capacity: layers one entry can reach
+    int es4;            // float4 words per layered entry: 3 + ceil(C / 4) (features) or 3
+    int C;              // feature row length (FEATURES) or 0
+    const float* features;
+    float4* lent;       // column with ids [e0, e0 + cnt) owns lent[e0 * zl * es4, (e0 + cnt) * zl * es4)
+    uint32_t* lmask;    // per layered entry: 8-bit mask of the layer's cells its cutoff sphere reaches
+    uint2* lbins;       // (start relative to the column's layered segment, count) per (molecule, column, layer)
 };
 
 struct VoxParams {
@@ -118,9 +121,10 @@ struct VoxParams {
     const float* chan_radii;   // channel-wise features: kernel radius of channel c_begin
     const ColEntry* entries;   // expanded column lists (warp-cell kernel)
     int masks;                 // 1: entries carry precomputed cell masks
-    int cpe, ncell, use_lists; // per-cell lists (see ExpandParams)
-    const uint32_t* cidx;
-    const uint2* cbins;
+    int nlayers, zl, es4;      // layered entries (see ExpandParams)
+    const float4* lent;
+    const uint32_t* lmask;
+    const uint2* lbins;
     float* out;
 };
 
@@ -350,8 +354,7 @@ __global__ void mvx_bin_fill_kernel(const BinParams P, int groups) {
 constexpr int kExpandSmemMasks = 512;   // masks of the first 512 entries of a column stay in shared memory
 
 __global__ void __launch_bounds__(256) mvx_expand_kernel(const ExpandParams P) {
-    __shared__ unsigned long long s_mask[8 * kExpandSmemMasks];   // 32 KB
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (gw >= (long long)P.B * P.ncol) return;
     const int mol = (int)(gw / P.ncol), col = (int)(gw % P.ncol);
@@ -412,53 +415,150 @@ __global__ void __launch_bounds__(256) mvx_expand_kernel(const ExpandParams P) {
         float4* dst = reinterpret_cast<float4*>(P.entries + base + i);
         const float4* src = reinterpret_cast<const float4*>(&e);
         dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
-        if (i < (uint32_t)kExpandSmemMasks) s_mask[warp * kExpandSmemMasks + i] = mask;
     }
-    if (!P.masks || !P.build_lists) return;
-    // per-cell lists: for every cell of the column, the entries whose mask names it (order kept).
-    // pass 1 counts (lane = cell for the final prefix), pass 2 fills.
-    __syncwarp();
-    const unsigned long long* wm = s_mask + warp * kExpandSmemMasks;
-    auto mask_of = [&](uint32_t i) -> unsigned long long {
-        if (i < (uint32_t)kExpandSmemMasks) return wm[i];
-        const ColEntry* e = P.entries + base + i;   // rare: very long column lists re-read their masks
-        return (unsigned long long)e->mask_lo | ((unsigned long long)e->mask_hi << 32);
+}
+
+// ---------------------------------------------------------------------------------------------
+// expand (layered form, feeds the tile kernel): one warp per (molecule, column).  The column's atoms are
+// regrouped per 16-voxel z layer (an atom reaching two layers is written twice), each as a record that is
+// ready to use from shared memory: tile-relative fp32 position, cutoff band, Gaussian coefficient, packed
+// forbidden planes, type / radius, atom id, followed by its feature row; beside it an 8-bit mask of the
+// layer's 2 x 4 x 16-voxel cells its cutoff sphere reaches.  Order inside a layer = ascending atom id.
+// The voxelize kernel then stages a whole tile with ONE flat coalesced copy and no per-atom arithmetic.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mvx_expand_layers_kernel(const ExpandParams P) {
+    __shared__ uint32_t s_lm[8 * kExpandSmemMasks];   // layer masks of the first 512 atoms of each warp's column
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (gw >= (long long)P.B * P.ncol) return;
+    const int mol = (int)(gw / P.ncol), col = (int)(gw % P.ncol);
+    const uint2 bin = P.bins[gw];
+    if (bin.y == 0) return;
+    const size_t base = (size_t)P.mol_offsets[mol] * (size_t)P.maxcols + bin.x;
+    const size_t lbase = base * (size_t)P.zl;
+    float4* lent = P.lent + lbase * (size_t)P.es4;
+    uint32_t* lmask = P.lmask + lbase;
+    const int x0 = (col / P.ncx) * kTile, y0 = (col % P.ncx) * kTile;
+    const double ox0 = (double)x0 * P.res - P.half_width, oy0 = (double)y0 * P.res - P.half_width;
+    const float resf = (float)P.res;
+    const float bhx = 0.5f * (kCellX - 1) * resf, bhy = 0.5f * (kCellY - 1) * resf;
+    const int ncz_max = (P.tz + kCellZ - 1) / kCellZ;
+    const int nl = P.nlayers;
+
+    auto layer_z = [&](int L, int& lo, int& hi) {   // voxel z range [lo, hi) of global layer L (empty if lo >= hi)
+        const int zc = L / ncz_max, cz = L - zc * ncz_max;
+        const int z0 = zc * P.tz, z1 = min(P.dim, z0 + P.tz);
+        lo = z0 + cz * kCellZ;
+        hi = min(lo + kCellZ, z1);
     };
-    // counts: each lane accumulates popcounts per cell for its entries, then a warp reduction per cell
-    uint32_t my_cnt_lo = 0, my_cnt_hi = 0;   // lane c holds the count of cell c (lo: cells 0-31, hi: 32-63)
-    for (int c = 0; c < P.ncell; ++c) {
+    auto layer_ez2 = [&](float az, int lo, int hi) -> float {   // squared z distance to the layer's voxel-centre slab
+        const float bhz = 0.5f * (hi - lo - 1) * resf;
+        const float ez = fmaxf(fabsf(az - (lo * resf + bhz)) - bhz, 0.f);
+        return ez * ez;
+    };
+    auto band_of = [&](float r, float& r2hi, float& r2lo) {
+        const float r2 = r * r;
+        const float tau = r * P.tau_lin + r2 * P.tau_quad;
+        r2hi = r2 + tau; r2lo = r2 - tau;
+    };
+    auto layer_mask_of = [&](uint32_t i) -> uint32_t {
+        const AtomRec rec = P.recs[P.lists[base + i]];
+        float r2hi, r2lo;
+        band_of(rec.r, r2hi, r2lo);
+        const float lim = r2hi + 1e-4f * (1.f + r2hi);
+        const float az = (float)(rec.pz + P.half_width);
+        uint32_t m = 0u;
+        for (int L = 0; L < nl; ++L) {
+            int lo, hi;
+            layer_z(L, lo, hi);
+            if (lo >= hi || rec.zhi < lo || rec.zlo >= hi) continue;
+            if (layer_ez2(az, lo, hi) <= lim) m |= 1u << L;
+        }
+        return m;
+    };
+
+    uint32_t* wl = s_lm + warp * kExpandSmemMasks;
+    for (uint32_t i = lane; i < bin.y; i += 32) {
+        const uint32_t m = layer_mask_of(i);
+        if (i < (uint32_t)kExpandSmemMasks) wl[i] = m;
+    }
+    __syncwarp();
+    auto lm = [&](uint32_t i) -> uint32_t { return i < (uint32_t)kExpandSmemMasks ? wl[i] : layer_mask_of(i); };
+
+    uint32_t my_cnt = 0;   // lane L: atoms reaching layer L
+    for (int L = 0; L < nl; ++L) {
         uint32_t cnt = 0;
         for (uint32_t i0 = 0; i0 < bin.y; i0 += 32) {
             const uint32_t i = i0 + lane;
-            const bool in = i < bin.y && ((mask_of(i) >> c) & 1ull);
-            cnt += __popc(__ballot_sync(0xffffffffu, in));
+            cnt += __popc(__ballot_sync(0xffffffffu, i < bin.y && ((lm(i) >> L) & 1u)));
         }
-        if ((c & 31) == lane) { if (c < 32) my_cnt_lo = cnt; else my_cnt_hi = cnt; }
+        if (lane == L) my_cnt = cnt;
     }
-    // exclusive prefix over the cells (two 32-wide scans)
-    uint32_t x = my_cnt_lo;
+    uint32_t x = my_cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
-    const uint32_t off_lo = x - my_cnt_lo;
-    const uint32_t total_lo = __shfl_sync(0xffffffffu, x, 31);
-    x = my_cnt_hi;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
-    const uint32_t off_hi = total_lo + x - my_cnt_hi;
-    uint2* cb = P.cbins + (size_t)gw * P.ncell;
-    if (lane < P.ncell) cb[lane] = make_uint2(off_lo, my_cnt_lo);
-    if (lane + 32 < P.ncell) cb[lane + 32] = make_uint2(off_hi, my_cnt_hi);
-    uint32_t* seg = P.cidx + base * (size_t)P.cpe;
-    for (int c = 0; c < P.ncell; ++c) {
-        uint32_t pos = __shfl_sync(0xffffffffu, c < 32 ? off_lo : off_hi, c & 31);
-        const uint32_t n_c = __shfl_sync(0xffffffffu, c < 32 ? my_cnt_lo : my_cnt_hi, c & 31);
-        if (n_c == 0) continue;
+    const uint32_t my_off = x - my_cnt;
+    if (lane < nl) P.lbins[(size_t)gw * nl + lane] = make_uint2(my_off, my_cnt);
+
+    for (int L = 0; L < nl; ++L) {
+        uint32_t pos = __shfl_sync(0xffffffffu, my_off, L);
+        if (__shfl_sync(0xffffffffu, my_cnt, L) == 0) continue;
+        int lo, hi;
+        layer_z(L, lo, hi);
         for (uint32_t i0 = 0; i0 < bin.y; i0 += 32) {
             const uint32_t i = i0 + lane;
-            const bool in = i < bin.y && ((mask_of(i) >> c) & 1ull);
-            const uint32_t m = __ballot_sync(0xffffffffu, in);
-            if (in) seg[pos + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(base + i);
-            pos += __popc(m);
+            const bool in = i < bin.y && ((lm(i) >> L) & 1u);
+            const uint32_t bal = __ballot_sync(0xffffffffu, in);
+            if (in) {
+                const size_t slot = pos + __popc(bal & ((1u << lane) - 1u));
+                const uint32_t n = P.lists[base + i];
+                const AtomRec rec = P.recs[n];
+                const float r = rec.r;
+                float r2hi, r2lo;
+                band_of(r, r2hi, r2lo);
+                const double rs = (double)r * P.sigma;
+                const float kc = (float)(-0.5 * 1.4426950408889634 / (rs * rs));
+                const float ax = (float)(rec.px - ox0), ay = (float)(rec.py - oy0), az = (float)(rec.pz + P.half_width);
+                const int fx = rec.fx - x0, fy = rec.fy - y0;
+                const uint32_t forb = (uint32_t)((rec.fx >= 0 && fx >= 0 && fx < kTile) ? fx : 0xFF) |
+                                      ((uint32_t)((rec.fy >= 0 && fy >= 0 && fy < kTile) ? fy : 0xFF) << 8) |
+                                      ((uint32_t)(rec.fz >= 0 ? rec.fz : 0xFFFF) << 16);
+                // cells of this layer reached by the cutoff sphere: exact sphere / voxel-centre-box test
+                const float lim = r2hi + 1e-4f * (1.f + r2hi);
+                const float ez2 = layer_ez2(az, lo, hi);
+                uint32_t cm = 0u;
+#pragma unroll
+                for (int ix = 0; ix < kTile / kCellX; ++ix) {
+                    const float ex = fmaxf(fabsf(ax - ((ix * kCellX) * resf + bhx)) - bhx, 0.f);
+                    const float exz = fmaf(ex, ex, ez2);
+#pragma unroll
+                    for (int iy = 0; iy < kTile / kCellY; ++iy) {
+                        const float ey = fmaxf(fabsf(ay - ((iy * kCellY) * resf + bhy)) - bhy, 0.f);
+                        if (fmaf(ey, ey, exz) <= lim) cm |= 1u << (ix * (kTile / kCellY) + iy);
+                    }
+                }
+                float4* e = lent + slot * (size_t)P.es4;
+                e[0] = make_float4(ax, ay, az, r2hi);
+                e[1] = make_float4(r2lo, kc, __uint_as_float(forb),
+                                   P.mode == 1 ? __uint_as_float((uint32_t)P.types[n]) : r);
+                e[2] = make_float4(__uint_as_float(n), 0.f, 0.f, 0.f);
+                lmask[slot] = cm;
+                if (P.mode == 2) {
+                    const float* f = P.features + (size_t)n * P.C;
+                    const int nq = P.es4 - 3;
+                    if ((P.C & 3) == 0) {
+                        for (int q = 0; q < nq; ++q) e[3 + q] = __ldg(reinterpret_cast<const float4*>(f) + q);
+                    } else {
+                        for (int q = 0; q < nq; ++q) {
+                            float v[4];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) v[c] = (4 * q + c < P.C) ? __ldg(f + 4 * q + c) : 0.f;
+                            e[3 + q] = make_float4(v[0], v[1], v[2], v[3]);
+                        }
+                    }
+                }
+            }
+            pos += __popc(bal);
         }
     }
 }
@@ -943,33 +1043,60 @@ __global__ void __launch_bounds__(NT, (CH <= 8 ? 3 : 2) * (256 / NT)) mvx_voxeli
 
 
 // ---------------------------------------------------------------------------------------------
-// voxelize, "cell-list" form (the fast path: D % 4 == 0 and <= 64 cells per column).  The expand pass has
-// already built, per (molecule, column, cell), the ordered list of entries whose cutoff sphere reaches the
-// cell, so warps are fully independent here: no CTA-wide staging, no barriers.  A warp owns a cell of
-// 2 x 4 x 16 voxels (lane = 4 voxels along z): it copies the cell's entries (and feature rows) into its
-// private shared-memory slice, tests them against its voxels (bitmask per lane) and then each lane walks
-// its own hits in ascending order, accumulating CH channels in registers; one 128-bit store per channel.
+// voxelize, "tile" form (the main path; needs D % 4 == 0).  One CTA per tile of 8 x 8 x tz voxels.
+//   0. staging: ONE flat, coalesced copy of the tile's layered entries (records + feature rows, prepared by
+//      mvx_expand_layers_kernel) and of their 8-bit cell masks into shared memory — no per-atom arithmetic,
+//      a single global round trip;
+//   1. a warp owns a cell of 2 x 4 x 16 voxels (lane = one float4 along z) and compacts, from ITS layer's
+//      sub-range only, the atoms whose mask names the cell into a warp-private list (32 atoms per ballot);
+//   2. every lane tests that short list against the nearest of its 4 voxels -> hit bitmask;
+//   3. each lane walks its own set bits in ascending order (the reference's atom order) and accumulates
+//      CH channels in registers: the accumulation runs max-hits-per-lane times per warp, not once per atom
+//      that touches any lane;
+//   4. one 128-bit streaming store per channel per lane.  Empty tiles are zero-filled division-free.
 // ---------------------------------------------------------------------------------------------
-template <int MODE, int CH>
-constexpr size_t lists_smem_bytes() {
-    return (size_t)(kThreads / 32) * kWarpList * (2 * sizeof(float4) + sizeof(int) + (MODE == 2 ? feat_stride<CH>() * sizeof(float) : 0));
+constexpr int kStageMaxEntries = 512;
+template <int MODE>
+__host__ __device__ constexpr int stage_bytes() { return MODE == 2 ? 60 * 1024 : 24 * 1024; }
+template <int MODE>
+constexpr size_t tiles_smem_bytes() {
+    return (size_t)stage_bytes<MODE>() + kStageMaxEntries * sizeof(uint32_t) + 4 * sizeof(uint2) +
+           (kThreads / 32) * kWarpList * (2 * sizeof(float4) + sizeof(uint16_t));
+}
+
+__device__ __forceinline__ void zero_fill_tile(float* out_mol, size_t plane, int D, int x0, int y0, int z0, int z1,
+                                               int c_begin, int c_end, int tid) {
+    const int lz = (z1 - z0) >> 2;
+    const int nitems = kTile * kTile * lz;
+    const int qstep = kThreads / lz, rstep = kThreads - qstep * lz;
+    int row = tid / lz, lzi = tid - row * lz;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int item = tid; item < nitems; item += kThreads) {
+        const int x = x0 + (row >> 3), y = y0 + (row & 7);
+        if (x < D && y < D) {
+            float* p = out_mol + (size_t)c_begin * plane + ((size_t)x * D + y) * D + z0 + lzi * 4;
+            for (int ch = c_begin; ch < c_end; ++ch, p += plane) __stcs(reinterpret_cast<float4*>(p), zero);
+        }
+        row += qstep; lzi += rstep;
+        if (lzi >= lz) { lzi -= lz; ++row; }
+    }
 }
 
 template <int MODE, int CH, bool BINARY>
-__global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_lists_kernel(const VoxParams P) {
+__global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_tiles_kernel(const VoxParams P) {
     constexpr int LPR = 4, RX = kCellX, RY = kCellY, CZ = kCellZ;
     constexpr int NCY = kTile / RY;
     constexpr int NW = kThreads / 32;
-    constexpr int FS = feat_stride<CH>();
-    constexpr int WBYTES = kWarpList * (2 * sizeof(float4) + sizeof(int) + (MODE == 2 ? FS * sizeof(float) : 0));
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float4* wA = reinterpret_cast<float4*>(smem_raw + (size_t)warp * WBYTES);
-    float4* wB = wA + kWarpList;
-    int* wN = reinterpret_cast<int*>(wB + kWarpList);
-    float* wF = reinterpret_cast<float*>(wN + kWarpList);
+    float4* sE = reinterpret_cast<float4*>(smem_raw);                                   // staged layered entries
+    uint32_t* sM = reinterpret_cast<uint32_t*>(smem_raw + stage_bytes<MODE>());         // their cell masks
+    uint2* sL = reinterpret_cast<uint2*>(sM + kStageMaxEntries);                        // layer sub-ranges (start, end)
+    float4* wA_all = reinterpret_cast<float4*>(sL + 4);
+    float4* wB_all = wA_all + NW * kWarpList;
+    uint16_t* wI_all = reinterpret_cast<uint16_t*>(wB_all + NW * kWarpList);
 
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int t = blockIdx.x;
     const int zc = t % P.nzc; t /= P.nzc;
     const int col = t % P.ncol;
@@ -980,49 +1107,58 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_lists_kernel(const V
     const size_t plane = (size_t)D * D * D;
     float* out_mol = P.out + (size_t)mol * P.Cout * plane;
 
-    const uint2 bin = P.bins[(size_t)mol * P.ncol + col];
-
-    if (bin.y == 0) {   // empty column: pure zero fill, one address computation per thread item
-        const int lz = (z1 - z0) >> 2;
-        const int nitems = kTile * kTile * lz;
-        const int qstep = kThreads / lz, rstep = kThreads - qstep * lz;
-        int row = tid / lz, lzi = tid - row * lz;
-        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int item = tid; item < nitems; item += kThreads) {
-            const int x = x0 + (row >> 3), y = y0 + (row & 7);
-            if (x < D && y < D) {
-                float* p = out_mol + (size_t)P.c_begin * plane + ((size_t)x * D + y) * D + z0 + lzi * 4;
-                for (int ch = P.c_begin; ch < P.c_end; ++ch, p += plane) __stcs(reinterpret_cast<float4*>(p), zero);
-            }
-            row += qstep; lzi += rstep;
-            if (lzi >= lz) { lzi -= lz; ++row; }
-        }
+    const size_t gcol = (size_t)mol * P.ncol + col;
+    const uint2 bin = P.bins[gcol];
+    if (bin.y == 0) {   // empty column
+        zero_fill_tile(out_mol, plane, D, x0, y0, z0, z1, P.c_begin, P.c_end, tid);
         return;
     }
-
     const int ncz_max = (P.tz + CZ - 1) / CZ;
-    const uint2* cb = P.cbins + ((size_t)mol * P.ncol + col) * P.ncell + (size_t)zc * ncz_max * kCellsXY;
-    const uint32_t* seg = P.cidx + ((size_t)P.mol_offsets[mol] * (size_t)P.maxcols + bin.x) * (size_t)P.cpe;
+    const int ncz = (z1 - z0 + CZ - 1) / CZ;
+    const uint2* lb = P.lbins + gcol * P.nlayers + (size_t)zc * ncz_max;
+    const uint2 lb_first = lb[0], lb_last = lb[ncz - 1];
+    const int seg_start = (int)lb_first.x;
+    const int total = (int)(lb_last.x + lb_last.y) - seg_start;   // layers of a chunk are consecutive
+    if (total == 0) {   // the column has atoms, none reaches this z chunk
+        zero_fill_tile(out_mol, plane, D, x0, y0, z0, z1, P.c_begin, P.c_end, tid);
+        return;
+    }
+    if (tid < ncz) {
+        const uint2 v = lb[tid];
+        sL[tid] = make_uint2(v.x - seg_start, v.x - seg_start + v.y);
+    }
+    const int ES4 = P.es4;
+    const int SC = min(kStageMaxEntries, stage_bytes<MODE>() / (ES4 * (int)sizeof(float4)));
+    const size_t colseg = ((size_t)P.mol_offsets[mol] * (size_t)P.maxcols + bin.x) * (size_t)P.zl + seg_start;
+    const float4* src = P.lent + colseg * (size_t)ES4;
+    const uint32_t* msrc = P.lmask + colseg;
+    const bool single_round = total <= SC;
+    bool staged = false;
+
+    float4* wA = wA_all + warp * kWarpList;
+    float4* wB = wB_all + warp * kWarpList;
+    uint16_t* wI = wI_all + warp * kWarpList;
+
     const float resf = (float)P.res;
     const float inv_res = 1.0f / resf;
     const int row = lane / LPR, zq = lane % LPR;
     const int rx = row / RY, ry = row % RY;
-    const int ncz = (z1 - z0 + CZ - 1) / CZ;
     const int ncells = kCellsXY * ncz;
-    const bool vec_feat = (P.C % 4) == 0;
 
     for (int c0 = P.c_begin; c0 < P.c_end; c0 += CH) {
-        for (int cell = warp; cell < ncells; cell += NW) {
+        for (int cell0 = 0; cell0 < ncells; cell0 += NW) {
+            const int cell = cell0 + warp;
+            const bool cell_ok = cell < ncells;
             const int cz = cell / kCellsXY, cxy = cell % kCellsXY;
             const int cxl = cxy / NCY, cyl = cxy % NCY;
             const int lx = cxl * RX + rx, ly = cyl * RY + ry, lzv = cz * CZ + zq * 4;
             const int x = x0 + lx, y = y0 + ly, z = z0 + lzv;
-            const bool valid = x < D && y < D && z < z1;
+            const bool valid = cell_ok && x < D && y < D && z < z1;
             const uint32_t lane_key = (uint32_t)lx | ((uint32_t)ly << 8);
-            const float ox = (float)((double)lx * P.res), oy = (float)((double)ly * P.res);
+            const float ox = (float)lx * resf, oy = (float)ly * resf;
             float oz[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) oz[k] = (float)((double)(z + k) * P.res);   // grid-absolute, like ColEntry::az
+            for (int k = 0; k < 4; ++k) oz[k] = (float)(z + k) * resf;   // grid-absolute, like the entries' z
 
             float acc[CH][4];
 #pragma unroll
@@ -1030,124 +1166,138 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_lists_kernel(const V
 #pragma unroll
                 for (int k = 0; k < 4; ++k) acc[c][k] = 0.f;
 
-            const uint2 cbin = cb[cell];
-            for (uint32_t j0 = 0; j0 < cbin.y; j0 += kWarpList) {
-                const int wn = (int)min((uint32_t)kWarpList, cbin.y - j0);
-                // 1. this warp's candidates: entries (and feature rows) -> warp-private shared memory
-                for (int jj = lane; jj < wn; jj += 32) {
-                    const float4* src = reinterpret_cast<const float4*>(P.entries + seg[cbin.x + j0 + jj]);
-                    float4 e0 = src[0], e1 = src[1];
-                    const int n = (int)__float_as_uint(src[2].x);
+            for (int r0 = 0; r0 < total; r0 += SC) {
+                const int nc = min(SC, total - r0);
+                if (!(single_round && staged)) {
+                    __syncthreads();
+                    const float4* g = src + (size_t)r0 * ES4;
+                    const int nq = nc * ES4;
+                    for (int q = tid; q < nq; q += kThreads) sE[q] = g[q];
+                    for (int i = tid; i < nc; i += kThreads) sM[i] = msrc[r0 + i];
+                    __syncthreads();
                     if (MODE == 2 && P.chan_radii != nullptr) {   // channel-wise features: this channel's radius
                         const float r = P.chan_radii[c0];
                         const float r2 = r * r;
                         const float tau = r * P.tau_lin + r2 * P.tau_quad;
                         const double rs = (double)r * P.sigma;
-                        e0.w = r2 + tau; e1.x = r2 - tau; e1.y = (float)(-0.5 * 1.4426950408889634 / (rs * rs));
-                        e1.w = r;
+                        const float kc = (float)(-0.5 * 1.4426950408889634 / (rs * rs));
+                        for (int i = tid; i < nc; i += kThreads) {
+                            sE[i * ES4].w = r2 + tau;
+                            float4 b = sE[i * ES4 + 1];
+                            b.x = r2 - tau; b.y = kc; b.w = r;
+                            sE[i * ES4 + 1] = b;
+                        }
+                        __syncthreads();
                     }
-                    wA[jj] = e0; wB[jj] = e1; wN[jj] = n;
-                    if (MODE == 2) {
-                        const float* f = P.features + (size_t)n * P.C + c0;
-                        float* d = wF + jj * FS;
-                        if (vec_feat && CH >= 4) {
-#pragma unroll
-                            for (int c4 = 0; c4 < CH; c4 += 4)
-                                *reinterpret_cast<float4*>(d + c4) =
-                                    (c0 + c4 < P.C) ? __ldg(reinterpret_cast<const float4*>(f + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < CH; ++c) d[c] = (c0 + c < P.C) ? __ldg(f + c) : 0.f;
+                    staged = true;
+                }
+                if (!cell_ok) continue;   // warp-uniform
+
+                const uint2 lr = sL[cz];
+                int base = max((int)lr.x, r0) - r0;
+                const int end = min((int)lr.y, r0 + nc) - r0;
+                while (base < end) {
+                    // 1. warp filter over this cell's layer: atoms whose mask names the cell, order kept
+                    int wn = 0;
+                    while (base < end && wn <= kWarpList - 32) {
+                        const int i = base + lane;
+                        const bool in = (i < end) && ((sM[i] >> cxy) & 1u);
+                        const uint32_t m = __ballot_sync(0xffffffffu, in);
+                        if (in) {
+                            const int pos = wn + __popc(m & ((1u << lane) - 1u));
+                            wA[pos] = sE[i * ES4]; wB[pos] = sE[i * ES4 + 1]; wI[pos] = (uint16_t)i;
                         }
+                        wn += __popc(m);
+                        base += 32;
                     }
-                }
-                __syncwarp();
-                // 2. every lane tests the list against the nearest of its 4 voxels; candidate hits -> bitmasks
-                uint32_t mask_lo = 0u, mask_hi = 0u;
-                if (valid) {
-                    auto near_hit = [&](const float4 A) -> bool {
-                        const float dx = A.x - ox, dy = A.y - oy;
-                        const float tz_ = A.z - oz[0];
-                        const float dzc = fmaf(-resf, fminf(fmaxf(rintf(tz_ * inv_res), 0.f), 3.f), tz_);
-                        return fmaf(dzc, dzc, fmaf(dx, dx, dy * dy)) <= A.w;
-                    };
-                    const int n_lo = min(wn, 32);
+                    __syncwarp();
+                    // 2. every lane tests the warp list against the nearest of its 4 voxels -> hit bitmasks
+                    uint32_t mask_lo = 0u, mask_hi = 0u;
+                    if (valid) {
+                        auto near_hit = [&](const float4 A) -> bool {
+                            const float dx = A.x - ox, dy = A.y - oy;
+                            const float tz_ = A.z - oz[0];
+                            const float dzc = fmaf(-resf, fminf(fmaxf(rintf(tz_ * inv_res), 0.f), 3.f), tz_);
+                            return fmaf(dzc, dzc, fmaf(dx, dx, dy * dy)) <= A.w;
+                        };
+                        const int n_lo = min(wn, 32);
 #pragma unroll 4
-                    for (int j = 0; j < n_lo; ++j)
-                        if (near_hit(wA[j])) mask_lo |= 1u << j;
+                        for (int j = 0; j < n_lo; ++j)
+                            if (near_hit(wA[j])) mask_lo |= 1u << j;
 #pragma unroll 4
-                    for (int j = 32; j < wn; ++j)
-                        if (near_hit(wA[j])) mask_hi |= 1u << (j - 32);
-                }
-                // 3. lane-private walk over the set bits, ascending (fixed fp32 summation order)
-                while (__any_sync(0xffffffffu, (mask_lo | mask_hi) != 0u)) {
-                    if ((mask_lo | mask_hi) != 0u) {
-                        int j;
-                        if (mask_lo != 0u) { j = __ffs((int)mask_lo) - 1; mask_lo &= mask_lo - 1u; }
-                        else { j = 31 + __ffs((int)mask_hi); mask_hi &= mask_hi - 1u; }
-                        const float4 A = wA[j];
-                        const float4 Bv = wB[j];
-                        const float dx = A.x - ox, dy = A.y - oy;
-                        const float dxy = fmaf(dx, dx, dy * dy);
-                        bool off[4] = {false, false, false, false};
-                        if (P.cull) {   // uniform: block-cull emulation, voxels on the atom's forbidden planes take nothing
-                            const uint32_t forb = __float_as_uint(Bv.z);
-                            const uint32_t tx = forb ^ lane_key;
-                            const bool row_off = (tx & 0xFFu) == 0u || (tx & 0xFF00u) == 0u;
-                            const int dzf = (int)(forb >> 16) - z;
+                        for (int j = 32; j < wn; ++j)
+                            if (near_hit(wA[j])) mask_hi |= 1u << (j - 32);
+                    }
+                    // 3. lane-private walk over the set bits, ascending (fixed fp32 summation order)
+                    while (__any_sync(0xffffffffu, (mask_lo | mask_hi) != 0u)) {
+                        if ((mask_lo | mask_hi) != 0u) {
+                            int j;
+                            if (mask_lo != 0u) { j = __ffs((int)mask_lo) - 1; mask_lo &= mask_lo - 1u; }
+                            else { j = 31 + __ffs((int)mask_hi); mask_hi &= mask_hi - 1u; }
+                            const float4 A = wA[j];
+                            const float4 Bv = wB[j];
+                            const float dx = A.x - ox, dy = A.y - oy;
+                            const float dxy = fmaf(dx, dx, dy * dy);
+                            bool off[4] = {false, false, false, false};
+                            if (P.cull) {   // uniform: block-cull emulation, voxels on the atom's forbidden planes take nothing
+                                const uint32_t forb = __float_as_uint(Bv.z);
+                                const uint32_t tx = forb ^ lane_key;
+                                const bool row_off = (tx & 0xFFu) == 0u || (tx & 0xFF00u) == 0u;
+                                const int dzf = (int)(forb >> 16) - z;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) off[k] = row_off || dzf == k;
-                        }
-                        // band centre / half width: |s - r^2| <= tau decides "replay in fp64"
-                        const float r2c = 0.5f * (A.w + Bv.x), tauh = 0.5f * (A.w - Bv.x) * 1.0001f + 1e-12f;
-                        float sk[4], w[4], dmin = 3.0e38f;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float dz = A.z - oz[k];
-                            sk[k] = fmaf(dz, dz, dxy);
-                            w[k] = (sk[k] < Bv.x && !off[k]) ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
-                            dmin = fminf(dmin, fabsf(sk[k] - r2c));
-                        }
-                        if (dmin <= tauh) {   // rare: voxels inside the tolerance band replay the reference's fp64 arithmetic
-                            const int n = wN[j];
-                            const float r32 = (MODE == 1) ? P.recs[n].r : Bv.w;
+                                for (int k = 0; k < 4; ++k) off[k] = row_off || dzf == k;
+                            }
+                            // |s - r^2| <= tau (slightly widened) for any of the 4 voxels -> replay in fp64
+                            const float r2c = 0.5f * (A.w + Bv.x), tauh = 0.5f * (A.w - Bv.x) * 1.0001f + 1e-12f;
+                            float sk[4], w[4], dmin = 3.0e38f;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                if (sk[k] >= Bv.x && !off[k]) {
-                                    const bool hit = sk[k] <= A.w && exact_hit(P.recs + n, r32, x, y, z + k, P.res, P.half_width);
-                                    w[k] = hit ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
+                                const float dz = A.z - oz[k];
+                                sk[k] = fmaf(dz, dz, dxy);
+                                w[k] = (sk[k] < Bv.x && !off[k]) ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
+                                dmin = fminf(dmin, fabsf(sk[k] - r2c));
+                            }
+                            const float4* ent = sE + (int)wI[j] * ES4;
+                            if (dmin <= tauh) {   // rare
+                                const int n = (int)__float_as_uint(ent[2].x);
+                                const float r32 = (MODE == 1) ? P.recs[n].r : Bv.w;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if (sk[k] >= Bv.x && !off[k]) {
+                                        const bool hit = sk[k] <= A.w && exact_hit(P.recs + n, r32, x, y, z + k, P.res, P.half_width);
+                                        w[k] = hit ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
+                                    }
                                 }
                             }
-                        }
-                        if (MODE == 0) {
+                            if (MODE == 0) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) acc[0][k] += w[k];
-                        } else if (MODE == 1) {
-                            const int ct = __float_as_int(Bv.w) - c0;
+                                for (int k = 0; k < 4; ++k) acc[0][k] += w[k];
+                            } else if (MODE == 1) {
+                                const int ct = __float_as_int(Bv.w) - c0;
 #pragma unroll
-                            for (int c = 0; c < CH; ++c)
+                                for (int c = 0; c < CH; ++c)
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) acc[c][k] += (ct == c) ? w[k] : 0.f;
-                        } else {
-                            const float* frow = wF + j * FS;
+                                    for (int k = 0; k < 4; ++k) acc[c][k] += (ct == c) ? w[k] : 0.f;
+                            } else if (CH >= 4) {
+                                const float4* frow = ent + 3 + (c0 >> 2);
 #pragma unroll
-                            for (int c4 = 0; c4 < CH; c4 += 4) {
-                                float f[4];
-                                if (CH >= 4) {
-                                    const float4 fv = *reinterpret_cast<const float4*>(frow + c4);
-                                    f[0] = fv.x; f[1] = fv.y; f[2] = fv.z; f[3] = fv.w;
-                                } else {
-                                    f[0] = frow[0]; f[1] = f[2] = f[3] = 0.f;
+                                for (int c4 = 0; c4 < CH; c4 += 4) {
+                                    const float4 fv = frow[c4 >> 2];
+                                    const float f[4] = {fv.x, fv.y, fv.z, fv.w};
+#pragma unroll
+                                    for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) acc[c4 + cc][k] = fmaf(f[cc], w[k], acc[c4 + cc][k]);
                                 }
+                            } else {
+                                const float f = reinterpret_cast<const float*>(ent + 3)[c0];
 #pragma unroll
-                                for (int cc = 0; cc < 4 && c4 + cc < CH; ++cc)
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) acc[c4 + cc][k] = fmaf(f[cc], w[k], acc[c4 + cc][k]);
+                                for (int k = 0; k < 4; ++k) acc[0][k] = fmaf(f, w[k], acc[0][k]);
                             }
                         }
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             if (valid) {
                 float* p = out_mol + (size_t)c0 * plane + ((size_t)x * D + y) * D + z;

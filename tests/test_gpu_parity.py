@@ -238,7 +238,7 @@ def test_dense_cluster_overflows_staging_and_warp_lists(mode):
         assert np.array_equal(out, ovox.forward_features(coords, None, feats, 1.0))
 
 
-@pytest.mark.parametrize("kernel", ["rows", "cells", "lists"])
+@pytest.mark.parametrize("kernel", ["rows", "cells", "tiles"])
 @pytest.mark.parametrize("lpr", ["2", "4"])
 def test_kernel_variants_agree_bitwise(kernel, lpr, monkeypatch):
     """Every kernel form / cell shape gives the same bits (binary) on a mixed batch."""
