@@ -298,3 +298,75 @@ def test_pipelined_host_path_matches_blocking():
         coords, offs, types, radii = batches[0]
         vox.forward_types_batch(coords, offs, None, types + 7, radii, 5, non_blocking=True)
         vox.check_status()
+
+
+ODD_SHAPES = [
+    # dim, res, mode, C, radii_type, rmax, V, density, blockdim
+    (12, 0.5, "types", 3, "scalar", 1.0, 60, "binary", None),
+    (100, 0.4, "types", 20, "atom-wise", 2.0, 500, "binary", None),       # two z chunks of 52 -> layers 16,16,16,4
+    (130, 0.5, "single", 1, "scalar", 1.5, 300, "binary", None),          # D % 4 != 0: scalar-store rows kernel
+    (36, 0.75, "features", 40, "scalar", 1.5, 400, "gaussian", None),     # 3 channel chunks
+    (36, 0.75, "features", 3, "atom-wise", 2.5, 400, "gaussian", 12),     # C < 4, big radii, blockdim 12
+    (44, 1.0, "features", 7, "channel-wise", 3.0, 200, "gaussian", None), # per-channel radii, coarse grid
+    (64, 0.25, "types", 9, "channel-wise", 1.2, 300, "gaussian", 64),     # fine grid, exact mode
+    (72, 0.5, "features", 16, "scalar", 1.0, 3000, "binary", None),       # two z chunks of 36, dense -> tile kernel
+]
+
+
+@pytest.mark.parametrize("dim,res,mode,C,radii_type,rmax,V,density,bd", ODD_SHAPES)
+def test_odd_shapes_vs_oracle(dim, res, mode, C, radii_type, rmax, V, density, bd):
+    rng = np.random.default_rng(dim * 1000 + C)
+    half = res * (dim - 1) / 2
+    B = 3
+    coords = rng.uniform(-half - 1, half + 1, size=(B * V, 3))
+    offs = np.arange(B + 1, dtype=np.int32) * V
+    centers = rng.normal(scale=0.3, size=(B, 3))
+    types = rng.integers(0, C, size=B * V).astype(np.int32) if mode == "types" else None
+    feats = rng.integers(0, 3, size=(B * V, C)).astype(np.float32) if mode == "features" else None
+    if radii_type == "scalar":
+        radii = float(rmax)
+    elif radii_type == "atom-wise":
+        radii = rng.uniform(0.5 * rmax, rmax, size=B * V).astype(np.float32)
+    else:
+        radii = rng.uniform(0.5 * rmax, rmax, size=C).astype(np.float32)
+    vox = mv.create_voxelizer(res, dim, radii_type, density, library="b200", blockdim=bd)
+    if mode == "types":
+        out = vox.forward_types_batch(coords, offs, centers, types, radii, C)
+    elif mode == "features":
+        out = vox.forward_features_batch(coords, offs, centers, feats, radii)
+    else:
+        out = vox.forward_single_batch(coords, offs, centers, radii)
+    vox.check_status()
+    ref = oracle_forward_batch(res, dim, radii_type, density, 0.5, bd or 8, mode, offs, coords, centers, types, feats,
+                               C, radii, num_threads=8)
+    _compare(out.cpu().numpy(), ref, density == "binary")
+
+
+@pytest.mark.parametrize("kernel", ["cells", "tiles", "rows"])
+def test_no_out_of_bounds_global_writes(kernel, monkeypatch):
+    """compute-sanitizer is closed on this GPU pool, so: sentinel guard bands around the output grid and the
+    workspace must survive a call untouched (catches stray global writes of any kernel)."""
+    monkeypatch.setenv("MVX_KERNEL", kernel)
+    rng = np.random.default_rng(17)
+    B = 4
+    counts = np.array([600, 0, 35, 1200])
+    offs = np.zeros(B + 1, dtype=np.int32)
+    offs[1:] = np.cumsum(counts)
+    N = int(offs[-1])
+    coords = rng.uniform(-9.5, 9.5, size=(N, 3))
+    feats = rng.uniform(size=(N, 12)).astype(np.float32)
+    radii = rng.uniform(0.8, 2.0, size=N).astype(np.float32)
+    vox = mv.create_voxelizer(0.5, 36, "atom-wise", "gaussian", library="b200")
+    ref = vox.forward_features_batch(coords, offs, None, feats, radii).clone()    # also sizes the workspace
+    ws_bytes = vox._ws.numel()
+    guard = 1 << 16
+    big_ws = torch.full((ws_bytes + 2 * guard,), 0xA5, dtype=torch.uint8, device="cuda")
+    vox._ws = big_ws[guard:guard + ws_bytes]
+    n_out = ref.numel()
+    big_out = torch.full((n_out + 2 * 4096,), float("nan"), dtype=torch.float32, device="cuda")
+    out = big_out[4096:4096 + n_out].view(ref.shape)
+    res = vox.forward_features_batch(coords, offs, None, feats, radii, out=out)
+    torch.cuda.synchronize()
+    assert res is out and torch.equal(out, ref)
+    assert bool(torch.isnan(big_out[:4096]).all()) and bool(torch.isnan(big_out[4096 + n_out:]).all())
+    assert bool((big_ws[:guard] == 0xA5).all()) and bool((big_ws[guard + ws_bytes:] == 0xA5).all())
