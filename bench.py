@@ -412,6 +412,20 @@ def run_b200_arm(args):
                      "step_share": {"prep_ms": prof["prep"], "bin_ms": prof["bin"], "voxelize_ms": prof["vox"]}},
         "clocks": clocks,
     }
+    if world == 1:   # the reference's own calling pattern: one molecule per call, host arrays in (cfg 1 shape)
+        a0, a1 = int(batch["offs"][0]), int(batch["offs"][1])
+        one = mv.create_voxelizer(w["res"], D, w["radii_type"], w["density"], library="b200", device=dev)
+        grid1 = one.get_empty_grid(C)
+        r1 = batch["radii"] if np.isscalar(batch["radii"]) else batch["radii"][a0:a1]
+        ch1 = channels_h[a0:a1]
+        lat = []
+        for k in range(60):
+            t0 = time.perf_counter()
+            one.forward(batch["coords"][a0:a1], batch["centers"][0], ch1, r1, out_grid=grid1)
+            torch.cuda.synchronize()
+            lat.append(time.perf_counter() - t0)
+        line["single_call"] = {"median_us": float(np.median(lat[10:]) * 1e6), "atoms": a1 - a0,
+                               "note": "Voxelizer.forward on one molecule with numpy inputs, synchronised (reference calling pattern)"}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_subprocess(name)
     print(json.dumps(line), flush=True)

@@ -107,7 +107,8 @@ int mvx_host_staging_bytes(const mvx_grid_spec *spec, const mvx_batch *batch, si
 int mvx_voxelize_host(const mvx_grid_spec *spec, const mvx_batch *host_batch, float *out, void *workspace,
                       size_t workspace_bytes, void *stream);
 
-/* Reads and clears the device status word of the last mvx_voxelize on this workspace (synchronises `stream`). */
+/* Reads the device status word of the last mvx_voxelize on this workspace (synchronises `stream`); the next
+ * mvx_voxelize on the workspace resets it. */
 int mvx_check_status(void *workspace, void *stream);
 
 /* Number of kernels one mvx_voxelize call launches for this spec/batch (bench.py's gpu_launches). */
