@@ -201,11 +201,6 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     return MVX_OK;
 }
 
-int env_lpr() {   // MVX_LPR=2|4: cell shape of the legacy CELLS form (experiments)
-    if (const char* e = std::getenv("MVX_LPR")) { int v = std::atoi(e); if (v == 2 || v == 4) return v; }
-    return 4;
-}
-
 template <typename K>
 cudaError_t set_smem(K kernel, size_t smem) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -219,17 +214,10 @@ cudaError_t launch_form(const mvx::VoxParams& vp, int form, int nv, unsigned gri
         if (!cfg) { cudaError_t e = set_smem(mvx::mvx_voxelize_tiles_kernel<MODE, CH, BINARY>, smem); if (e != cudaSuccess) return e; cfg = true; }
         mvx::mvx_voxelize_tiles_kernel<MODE, CH, BINARY><<<grid, mvx::kThreads, smem, st>>>(vp);
     } else if (form == FORM_CELLS) {
-        if (env_lpr() == 2) {
-            constexpr size_t smem = mvx::cells_smem_bytes<MODE, CH, 256>();
-            static bool cfg = false;
-            if (!cfg) { cudaError_t e = set_smem(mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, 2, 256>, smem); if (e != cudaSuccess) return e; cfg = true; }
-            mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, 2, 256><<<grid, 256, smem, st>>>(vp);
-        } else {
-            constexpr size_t smem = mvx::cells_smem_bytes<MODE, CH, 256>();
-            static bool cfg = false;
-            if (!cfg) { cudaError_t e = set_smem(mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, 4, 256>, smem); if (e != cudaSuccess) return e; cfg = true; }
-            mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, 4, 256><<<grid, 256, smem, st>>>(vp);
-        }
+        constexpr size_t smem = mvx::cells_smem_bytes<MODE, CH>();
+        static bool cfg = false;
+        if (!cfg) { cudaError_t e = set_smem(mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY>, smem); if (e != cudaSuccess) return e; cfg = true; }
+        mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY><<<grid, mvx::kThreads, smem, st>>>(vp);
     } else if (nv == 4) {
         mvx::mvx_voxelize_kernel<MODE, CH, BINARY, 4><<<grid, mvx::kThreads, 0, st>>>(vp);
     } else {
@@ -330,7 +318,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, 
     uint2* bins = (uint2*)(ws + pl.off_bins);
     uint32_t* lists = (uint32_t*)(ws + pl.off_lists);
     mvx::ColEntry* entries = (mvx::ColEntry*)(ws + pl.off_entries);
-    const bool legacy_masks = pl.masks && env_lpr() == 4;   // CELLS form: masks precomputed by expand
+    const bool legacy_masks = pl.masks;   // CELLS form: cell masks precomputed by expand (<= 64 cells per column)
 
     const int B = batch->num_mols;
     const int64_t N = batch->total_atoms;

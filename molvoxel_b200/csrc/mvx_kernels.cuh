@@ -765,16 +765,18 @@ constexpr uint32_t kNoForb = 0xFFFFFFFFu;
 template <int CH>
 __host__ __device__ constexpr int feat_stride() { return CH + 4; }   // +4 words: conflict-free lane-private LDS.128
 
-template <int MODE, int CH, int NT>
+template <int MODE, int CH>
 constexpr size_t cells_smem_bytes() {
+    constexpr int NT = kThreads;
     return (size_t)(2 * NT) * (2 * sizeof(float4) + sizeof(int) + sizeof(uint32_t)) +
            (NT / 32) * kWarpList * (2 * sizeof(float4) + sizeof(uint16_t)) + 32 * sizeof(float4) +
            (MODE == 2 ? (size_t)(2 * NT) * feat_stride<CH>() * sizeof(float) : 0);
 }
 
-template <int MODE, int CH, bool BINARY, int LPR, int NT>
-__global__ void __launch_bounds__(NT, (CH <= 8 ? 3 : 2) * (256 / NT)) mvx_voxelize_cells_kernel(const VoxParams P) {
-    constexpr int NW = NT / 32;   // warps per CTA
+template <int MODE, int CH, bool BINARY>
+__global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cells_kernel(const VoxParams P) {
+    constexpr int NT = kThreads, LPR = 4;   // 4 lanes (one float4 each) along z per row: cells of 2 x 4 x 16 voxels
+    constexpr int NW = NT / 32;             // warps per CTA
     constexpr int SC = 2 * NT;    // atoms staged per round
     constexpr int ROWS = 32 / LPR;
     constexpr int RY = (LPR >= 8) ? 2 : 4;

@@ -239,13 +239,9 @@ def test_dense_cluster_overflows_staging_and_warp_lists(mode):
 
 
 @pytest.mark.parametrize("kernel", ["rows", "cells", "tiles"])
-@pytest.mark.parametrize("lpr", ["2", "4"])
-def test_kernel_variants_agree_bitwise(kernel, lpr, monkeypatch):
-    """Every kernel form / cell shape gives the same bits (binary) on a mixed batch."""
-    if kernel != "cells" and lpr != "4":
-        pytest.skip("only the cells kernel has a selectable cell shape")
+def test_kernel_variants_agree_bitwise(kernel, monkeypatch):
+    """Every kernel form gives the same bits (binary) on a mixed batch."""
     monkeypatch.setenv("MVX_KERNEL", kernel)
-    monkeypatch.setenv("MVX_LPR", lpr)
     rng = np.random.default_rng(5)
     B = 6
     counts = np.array([0, 3, 50, 700, 1, 1500])
