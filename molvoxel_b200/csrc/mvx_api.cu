@@ -235,7 +235,7 @@ cudaError_t launch_density(const mvx::VoxParams& vp, bool binary, int form, int 
 // CTAs on the 148 SMs, otherwise enough groups to get there (at least 8 columns = one per warp each).
 int bin_groups(int B, int ncol) {
     if (B >= 296) return 1;
-    int g = (296 + B - 1) / (B > 0 ? B : 1);
+    int g = (1184 + B - 1) / (B > 0 ? B : 1);   // aim at ~8 CTAs per SM so the latency-bound scans overlap
     int gmax = (ncol + 7) / 8;
     if (g > gmax) g = gmax;
     return g < 1 ? 1 : g;
