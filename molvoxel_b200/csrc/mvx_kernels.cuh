@@ -591,6 +591,17 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
+// Two fp32 FMAs in one instruction (Blackwell FFMA2, PTX fma.rn.f32x2): d0 += a0*b, d1 += a1*b.  Each half is an
+// ordinary IEEE fp32 FMA, so results equal two scalar fmaf calls bit for bit.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b) {
+    unsigned long long a, bb, c;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(d0), "f"(d1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(bb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(c));
+}
+
 __device__ __forceinline__ void store_vox(float* p, const float (&v)[4]) {
     __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
 }
@@ -1017,10 +1028,16 @@ __global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cell
                                     } else {
                                         f[0] = frow[0]; f[1] = f[2] = f[3] = 0.f;
                                     }
+                                    if (CH >= 4) {   // channel pairs through the packed FMA
 #pragma unroll
-                                    for (int cc = 0; cc < 4 && c4 + cc < CH; ++cc)
+                                        for (int k = 0; k < 4; ++k) {
+                                            ffma2(acc[c4][k], acc[c4 + 1 < CH ? c4 + 1 : c4][k], f[0], f[1], w[k]);
+                                            ffma2(acc[c4 + 2 < CH ? c4 + 2 : c4][k], acc[c4 + 3 < CH ? c4 + 3 : c4][k], f[2], f[3], w[k]);
+                                        }
+                                    } else {
 #pragma unroll
-                                        for (int k = 0; k < 4; ++k) acc[c4 + cc][k] = fmaf(f[cc], w[k], acc[c4 + cc][k]);
+                                        for (int k = 0; k < 4; ++k) acc[0][k] = fmaf(f[0], w[k], acc[0][k]);
+                                    }
                                 }
                             }
                         }
@@ -1287,9 +1304,10 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_tiles_kernel(const V
                                     const float4 fv = frow[c4 >> 2];
                                     const float f[4] = {fv.x, fv.y, fv.z, fv.w};
 #pragma unroll
-                                    for (int cc = 0; cc < 4; ++cc)
-#pragma unroll
-                                        for (int k = 0; k < 4; ++k) acc[c4 + cc][k] = fmaf(f[cc], w[k], acc[c4 + cc][k]);
+                                    for (int k = 0; k < 4; ++k) {   // channel pairs through the packed FMA
+                                        ffma2(acc[c4][k], acc[c4 + 1][k], f[0], f[1], w[k]);
+                                        ffma2(acc[c4 + 2][k], acc[c4 + 3][k], f[2], f[3], w[k]);
+                                    }
                                 }
                             } else {
                                 const float f = reinterpret_cast<const float*>(ent + 3)[c0];
