@@ -302,11 +302,10 @@ class Voxelizer:
 
     def _forward_batch(self, mode, coords, mol_offsets, centers, channels, radii, C, random_translation,
                        random_rotation, out, infer_types_channels=False, max_radius=None, non_blocking=False):
-        if self.device.type != "cuda" or not torch.cuda.is_available():
-            raise RuntimeError("molvoxel_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        have_cuda = self.device.type == "cuda" and torch.cuda.is_available()
         coords, centers, channels, radii = _norm(coords), _norm(centers), _norm(channels), _norm(radii)
         on_device = isinstance(coords, torch.Tensor) and coords.is_cuda
-        if non_blocking and not on_device:
+        if non_blocking and not on_device and have_cuda:
             # pipelined host path: async H2D on the copy stream, then the no-sync device path
             if not _is_scalar(radii) and max_radius is None:
                 max_radius = float(np.asarray(radii).max()) if np.asarray(radii).size else 1.0
@@ -352,8 +351,8 @@ class Voxelizer:
             self._check_radii(mode, radii, N, C)
 
         if out is not None:
-            assert isinstance(out, torch.Tensor) and out.is_cuda and out.dtype == torch.float32 and out.is_contiguous(), \
-                "out_grid must be a contiguous float32 CUDA tensor"
+            assert isinstance(out, torch.Tensor) and out.dtype == torch.float32 and out.is_contiguous() and \
+                (out.is_cuda or not have_cuda), "out_grid must be a contiguous float32 CUDA tensor"
             if mode == "types":
                 assert out.shape[1] >= C, f"Output channel is less than number of types: {out.shape[1]} < {C}"
                 assert tuple(out.shape[2:]) == (D, D, D), \
@@ -369,6 +368,10 @@ class Voxelizer:
             out_channels = int(out.shape[1])
         else:
             out_channels = C
+        # every argument check of the reference has passed; from here on a CUDA device is required
+        if not have_cuda:
+            raise RuntimeError("molvoxel_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if out is None:
             out = torch.empty((B, out_channels, D, D, D), dtype=torch.float32, device=self.device)
 
         # centring stays inside the kernel (fp64 or numpy's fp32-fp32 promotion); the optional random

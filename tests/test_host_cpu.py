@@ -157,3 +157,49 @@ def test_two_rank_gloo_shard_and_gather():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True, 2.0), (1, True, 2.0)]
+
+
+def _cpu_vox(**kw):
+    return mv.create_voxelizer(0.5, 16, library="b200", **kw)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="argument checks are reached before the CUDA requirement")
+@pytest.mark.parametrize("call, msg", [
+    (lambda: _cpu_vox().forward_types(np.zeros((4, 3)), None, np.zeros(3, dtype=np.int16), 1.0),
+     "types does not match dimension"),
+    (lambda: _cpu_vox().forward_types(np.zeros((4, 3)), None, np.zeros(4, dtype=np.int16), np.ones(4, dtype=np.float32)),
+     "radii should be scalar"),
+    (lambda: _cpu_vox(radii_type="atom-wise").forward_types(np.zeros((4, 3)), None, np.zeros(4, dtype=np.int16), 1.0),
+     "radii should be Array"),
+    (lambda: _cpu_vox(radii_type="atom-wise").forward_single(np.zeros((4, 3)), None, np.ones(3, dtype=np.float32)),
+     "radii does not match dimension (number of atoms,)"),
+    (lambda: _cpu_vox(radii_type="channel-wise").forward_features(np.zeros((4, 3)), None, np.zeros((4, 5), dtype=np.float32),
+                                                                np.ones(4, dtype=np.float32)),
+     "radii does not match dimension (number of channels,)"),
+    (lambda: _cpu_vox(radii_type="channel-wise").forward_single(np.zeros((4, 3)), None, np.ones(1, dtype=np.float32)),
+     "Channel-Wise Radii Type is not supported"),
+    (lambda: _cpu_vox().forward_features(np.zeros((4, 3)), None, np.zeros((3, 5), dtype=np.float32), 1.0),
+     "atom features does not match number of atoms"),
+    (lambda: _cpu_vox().forward_types(np.zeros((4, 3)), None, np.array([0, 1, 2, 3]), 1.0, out_grid=torch.zeros(2, 16, 16, 16)),
+     "Output channel is less than number of types"),
+    (lambda: _cpu_vox().forward_features(np.zeros((4, 3)), None, np.zeros((4, 5), dtype=np.float32), 1.0,
+                                         out_grid=torch.zeros(4, 16, 16, 16)),
+     "Output grid dimension incorrect"),
+    (lambda: _cpu_vox().forward_single(np.zeros((4, 3)), None, 1.0, out_grid=torch.zeros(2, 16, 16, 16)),
+     "Output channel should be 1"),
+])
+def test_reference_argument_checks_and_messages(call, msg):
+    """Same AssertionError conditions and messages as reference numpy/voxelizer.py:171-192, :317-342, :438-455."""
+    with pytest.raises(AssertionError) as e:
+        call()
+    assert msg in str(e.value)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_valid_arguments_then_no_cpu_fallback_and_dispatch():
+    vox = _cpu_vox()
+    with pytest.raises(ValueError):   # np.max of an empty array, like the reference (numpy/voxelizer.py:325)
+        vox.forward_types(np.zeros((0, 3)), None, np.zeros((0,), dtype=np.int16), 1.0)
+    for channels in (None, np.zeros(4, dtype=np.int16), np.zeros((4, 2), dtype=np.float32)):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):   # forward() dispatches on channels' rank
+            vox(np.zeros((4, 3)), np.zeros(3), channels, 1.0)
