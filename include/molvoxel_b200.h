@@ -37,6 +37,7 @@ enum { MVX_DENSITY_GAUSSIAN = 0, MVX_DENSITY_BINARY = 1 };          /* base/voxe
 enum { MVX_RADII_SCALAR = 0, MVX_RADII_CHANNEL_WISE = 1, MVX_RADII_ATOM_WISE = 2 }; /* base/voxelizer.py:12 */
 enum { MVX_MODE_SINGLE = 0, MVX_MODE_TYPES = 1, MVX_MODE_FEATURES = 2 };            /* base/voxelizer.py:121-128 */
 enum { MVX_F32 = 0, MVX_F64 = 1 };
+enum { MVX_OUT_F32 = 0, MVX_OUT_BF16 = 1, MVX_OUT_F16 = 2 };   /* element type of the output grid */
 
 /* Constructor arguments of the reference Voxelizer (base/voxelizer.py:15-38, numpy/voxelizer.py:22-35). */
 typedef struct mvx_grid_spec {
@@ -84,17 +85,20 @@ typedef struct mvx_batch {
                                        the clip — the random rigid transform every reference forward_* takes
                                        (random_translation / random_rotation, numpy/voxelizer.py:265,
                                        numpy/transform.py:43-80), fused into the per-atom prep kernel. */
+    int32_t        out_dtype;       /* MVX_OUT_F32 (the reference's precision=32 layout, default) or a
+                                       reduced-precision grid: every voxel is computed in fp32 exactly as
+                                       for MVX_OUT_F32 and rounded once (nearest-even) on the store. */
 } mvx_batch;
 
 /* Bytes of device workspace mvx_voxelize needs for this spec/batch (256-byte aligned base). */
 int mvx_workspace_bytes(const mvx_grid_spec *spec, const mvx_batch *batch, size_t *out_bytes);
 
 /*
- * Voxelize a batch: out is a DEVICE buffer (B, out_channels, D, H, W) float32, contiguous,
+ * Voxelize a batch: out is a DEVICE buffer (B, out_channels, D, H, W) of batch->out_dtype (float32 by default), contiguous,
  * written exactly once per voxel (zeros included).  Work is enqueued on `stream`
  * (a cudaStream_t; NULL = legacy default stream); no host synchronisation happens inside.
  */
-int mvx_voxelize(const mvx_grid_spec *spec, const mvx_batch *batch, float *out, void *workspace,
+int mvx_voxelize(const mvx_grid_spec *spec, const mvx_batch *batch, void *out, void *workspace,
                  size_t workspace_bytes, void *stream);
 
 /*
@@ -104,7 +108,7 @@ int mvx_voxelize(const mvx_grid_spec *spec, const mvx_batch *batch, float *out, 
  * Pinned host memory makes the copies asynchronous but is not required.
  */
 int mvx_host_staging_bytes(const mvx_grid_spec *spec, const mvx_batch *batch, size_t *out_bytes);
-int mvx_voxelize_host(const mvx_grid_spec *spec, const mvx_batch *host_batch, float *out, void *workspace,
+int mvx_voxelize_host(const mvx_grid_spec *spec, const mvx_batch *host_batch, void *out, void *workspace,
                       size_t workspace_bytes, void *stream);
 
 /* Reads the device status word of the last mvx_voxelize on this workspace (synchronises `stream`); the next

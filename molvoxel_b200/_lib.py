@@ -28,6 +28,7 @@ MVX_F32, MVX_F64 = 0, 1
 DENSITY = {"gaussian": 0, "binary": 1}
 RADII = {"scalar": 0, "channel-wise": 1, "atom-wise": 2}
 MODE = {"single": 0, "types": 1, "features": 2}
+OUT_DTYPE = {"float32": 0, "bfloat16": 1, "float16": 2}
 
 
 class GridSpec(ctypes.Structure):
@@ -59,6 +60,7 @@ class Batch(ctypes.Structure):
         ("radii", ctypes.c_void_p),
         ("max_radius", ctypes.c_double),
         ("transforms", ctypes.c_void_p),
+        ("out_dtype", ctypes.c_int32),
     ]
 
 

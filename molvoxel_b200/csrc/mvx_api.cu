@@ -74,6 +74,7 @@ int check_args(const mvx_grid_spec* s, const mvx_batch* b) {
     if (b->out_channels < C)   // numpy/voxelizer.py:337 (types), :192 (features), :450 (single)
         return fail(MVX_ERR_BAD_SHAPE, "Output channel is less than number of types");
     if (b->mode != MVX_MODE_TYPES && b->out_channels != C) return fail(MVX_ERR_BAD_SHAPE, "Output grid dimension incorrect");
+    if (b->out_dtype < MVX_OUT_F32 || b->out_dtype > MVX_OUT_F16) return fail(MVX_ERR_BAD_ENUM, "out_dtype");
     if (b->num_mols > 0 && !b->mol_offsets) return fail(MVX_ERR_NULL_POINTER, "mol_offsets");
     if (b->total_atoms > 0) {
         if (!b->coords) return fail(MVX_ERR_NULL_POINTER, "coords");
@@ -206,24 +207,30 @@ cudaError_t set_smem(K kernel, size_t smem) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
-template <int MODE, int CH, bool BINARY>
-cudaError_t launch_form(const mvx::VoxParams& vp, int form, int nv, unsigned grid, cudaStream_t st) {
+template <int MODE, int CH, bool BINARY, bool O16>
+cudaError_t launch_form_out(const mvx::VoxParams& vp, int form, int nv, unsigned grid, cudaStream_t st) {
     if (form == FORM_TILES) {
         constexpr size_t smem = mvx::tiles_smem_bytes<MODE>();
         static bool cfg = false;
-        if (!cfg) { cudaError_t e = set_smem(mvx::mvx_voxelize_tiles_kernel<MODE, CH, BINARY>, smem); if (e != cudaSuccess) return e; cfg = true; }
-        mvx::mvx_voxelize_tiles_kernel<MODE, CH, BINARY><<<grid, mvx::kThreads, smem, st>>>(vp);
+        if (!cfg) { cudaError_t e = set_smem(mvx::mvx_voxelize_tiles_kernel<MODE, CH, BINARY, O16>, smem); if (e != cudaSuccess) return e; cfg = true; }
+        mvx::mvx_voxelize_tiles_kernel<MODE, CH, BINARY, O16><<<grid, mvx::kThreads, smem, st>>>(vp);
     } else if (form == FORM_CELLS) {
         constexpr size_t smem = mvx::cells_smem_bytes<MODE, CH>();
         static bool cfg = false;
-        if (!cfg) { cudaError_t e = set_smem(mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY>, smem); if (e != cudaSuccess) return e; cfg = true; }
-        mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY><<<grid, mvx::kThreads, smem, st>>>(vp);
+        if (!cfg) { cudaError_t e = set_smem(mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, O16>, smem); if (e != cudaSuccess) return e; cfg = true; }
+        mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, O16><<<grid, mvx::kThreads, smem, st>>>(vp);
     } else if (nv == 4) {
-        mvx::mvx_voxelize_kernel<MODE, CH, BINARY, 4><<<grid, mvx::kThreads, 0, st>>>(vp);
+        mvx::mvx_voxelize_kernel<MODE, CH, BINARY, 4, O16><<<grid, mvx::kThreads, 0, st>>>(vp);
     } else {
-        mvx::mvx_voxelize_kernel<MODE, CH, BINARY, 1><<<grid, mvx::kThreads, 0, st>>>(vp);
+        mvx::mvx_voxelize_kernel<MODE, CH, BINARY, 1, O16><<<grid, mvx::kThreads, 0, st>>>(vp);
     }
     return cudaGetLastError();
+}
+
+template <int MODE, int CH, bool BINARY>
+cudaError_t launch_form(const mvx::VoxParams& vp, int form, int nv, unsigned grid, cudaStream_t st) {
+    return vp.out_kind == 0 ? launch_form_out<MODE, CH, BINARY, false>(vp, form, nv, grid, st)
+                            : launch_form_out<MODE, CH, BINARY, true>(vp, form, nv, grid, st);
 }
 
 template <int MODE, int CH>
@@ -300,7 +307,7 @@ int mvx_launches_per_call(const mvx_grid_spec* spec, const mvx_batch* batch) {
     return (batch->total_atoms > 0 ? 1 : 0) + nbin + nexp + nvox;   // prep + bin + expand + voxelize
 }
 
-int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, void* workspace,
+int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, void* workspace,
                  size_t workspace_bytes, void* stream) {
     Plan pl;
     int rc = make_plan(spec, batch, &pl);
@@ -380,7 +387,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, float* out, 
         vp.dim = spec->dimension; vp.ncx = pl.geo.ncx; vp.ncol = pl.ncol; vp.nzc = pl.nzc; vp.tz = pl.tz;
         vp.C = C; vp.Cout = batch->out_channels; vp.maxcols = pl.maxcols; vp.cull = pl.geo.nb > 1;
         vp.mol_offsets = batch->mol_offsets; vp.recs = recs; vp.bins = bins; vp.lists = lists;
-        vp.types = batch->types; vp.features = batch->features; vp.chan_radii = nullptr; vp.out = out;
+        vp.types = batch->types; vp.features = batch->features; vp.chan_radii = nullptr; vp.out = out; vp.out_kind = batch->out_dtype;
         vp.entries = entries; vp.masks = legacy_masks;
         vp.nlayers = pl.nlayers; vp.zl = pl.zl; vp.es4 = pl.es4;
         vp.lent = (const float4*)(ws + pl.off_lent); vp.lmask = (const uint32_t*)(ws + pl.off_lmask);
@@ -476,7 +483,7 @@ int mvx_host_staging_bytes(const mvx_grid_spec* spec, const mvx_batch* batch, si
     return MVX_OK;
 }
 
-int mvx_voxelize_host(const mvx_grid_spec* spec, const mvx_batch* hb, float* out, void* workspace,
+int mvx_voxelize_host(const mvx_grid_spec* spec, const mvx_batch* hb, void* out, void* workspace,
                       size_t workspace_bytes, void* stream) {
     Plan pl;
     int rc = make_plan(spec, hb, &pl);

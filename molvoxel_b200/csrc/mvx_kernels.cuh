@@ -11,6 +11,8 @@
 //   AtomRec  40 B per atom: centred fp64 position, fp32 radius, cull "forbidden planes", z voxel range
 //   lists    uint32 atom ids per (molecule, 8x8 voxel column), ascending = the reference's atom order
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -125,7 +127,8 @@ struct VoxParams {
     const float4* lent;
     const uint32_t* lmask;
     const uint2* lbins;
-    float* out;
+    void* out;                 // (B, Cout, D, D, D), element type by out_kind
+    int out_kind;              // 0 fp32 (reference), 1 bf16, 2 fp16 (reduced-precision output)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -602,12 +605,61 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
     asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(c));
 }
 
-__device__ __forceinline__ void store_vox(float* p, const float (&v)[4]) {
-    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+// Output element size and stores.  fp32 is the reference layout; bf16 / fp16 round each finished voxel once
+// (round-to-nearest-even), halving the bytes that bound the op.
+template <bool O16>
+__device__ __forceinline__ void store_vox(char* p, const float (&v)[4], int kind) {
+    if (!O16) {
+        __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+    } else if (kind == 1) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+        __stcs(reinterpret_cast<uint2*>(p), make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b)));
+    } else {
+        const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+        __stcs(reinterpret_cast<uint2*>(p), make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b)));
+    }
 }
-__device__ __forceinline__ void store_vox(float* p, const float (&v)[1]) { __stcs(p, v[0]); }
+template <bool O16>
+__device__ __forceinline__ void store_vox(char* p, const float (&v)[1], int kind) {
+    if (!O16) __stcs(reinterpret_cast<float*>(p), v[0]);
+    else if (kind == 1) { const __nv_bfloat16 h = __float2bfloat16_rn(v[0]); *reinterpret_cast<__nv_bfloat16*>(p) = h; }
+    else { const __half h = __float2half_rn(v[0]); *reinterpret_cast<__half*>(p) = h; }
+}
 
-template <int MODE, int CH, bool BINARY, int NV>
+// Division-free zero fill of one tile (8 x 8 x [z0, z1) voxels, channels [c_begin, c_end)), 16-byte stores.
+// VPI voxels of ES bytes per thread item; the fp32 instance (4 x 4 B) is the hot path of ligand batches.
+template <int VPI, int ES>
+__device__ __forceinline__ void zero_fill_items(char* out_mol, size_t plane, int D, int x0, int y0, int z0, int z1,
+                                                int c_begin, int c_end, int tid) {
+    const int lz = (z1 - z0) / VPI;
+    const int nitems = kTile * kTile * lz;
+    const int qstep = kThreads / lz, rstep = kThreads - qstep * lz;
+    int row = tid / lz, lzi = tid - row * lz;
+    const size_t pstride = plane * ES;
+    for (int item = tid; item < nitems; item += kThreads) {
+        const int x = x0 + (row >> 3), y = y0 + (row & 7);
+        if (x < D && y < D) {
+            char* p = out_mol + ((size_t)c_begin * plane + ((size_t)x * D + y) * D + z0 + lzi * VPI) * ES;
+            if (VPI * ES == 16) {
+                for (int ch = c_begin; ch < c_end; ++ch, p += pstride) __stcs(reinterpret_cast<float4*>(p), make_float4(0.f, 0.f, 0.f, 0.f));
+            } else {
+                for (int ch = c_begin; ch < c_end; ++ch, p += pstride) __stcs(reinterpret_cast<uint2*>(p), make_uint2(0u, 0u));
+            }
+        }
+        row += qstep; lzi += rstep;
+        if (lzi >= lz) { lzi -= lz; ++row; }
+    }
+}
+
+template <bool O16>
+__device__ __forceinline__ void zero_fill_tile(char* out_mol, size_t plane, int D, int x0, int y0, int z0, int z1,
+                                               int c_begin, int c_end, int tid) {
+    if (!O16) zero_fill_items<4, 4>(out_mol, plane, D, x0, y0, z0, z1, c_begin, c_end, tid);
+    else if (((z1 - z0) & 7) == 0 && (D & 7) == 0) zero_fill_items<8, 2>(out_mol, plane, D, x0, y0, z0, z1, c_begin, c_end, tid);
+    else zero_fill_items<4, 2>(out_mol, plane, D, x0, y0, z0, z1, c_begin, c_end, tid);
+}
+
+template <int MODE, int CH, bool BINARY, int NV, bool O16>
 __global__ void __launch_bounds__(kThreads) mvx_voxelize_kernel(const VoxParams P) {
     __shared__ float4 sA[kMaxCand];   // rel x, rel y, rel z, r^2 + tau
     __shared__ float4 sB[kMaxCand];   // r^2 - tau, gaussian coefficient, forbidden planes, type | radius
@@ -625,7 +677,8 @@ __global__ void __launch_bounds__(kThreads) mvx_voxelize_kernel(const VoxParams 
     const int lz = (z1 - z0 + NV - 1) / NV;   // thread items per (x, y) row
     const int nitems = kTile * kTile * lz;
     const size_t plane = (size_t)D * D * D;
-    float* out_mol = P.out + (size_t)mol * P.Cout * plane;
+    constexpr int es = O16 ? 2 : 4;
+    char* out_mol = reinterpret_cast<char*>(P.out) + (size_t)mol * P.Cout * plane * es;
 
     const uint2 bin = P.bins[(size_t)mol * P.ncol + col];
     const int cnt = (int)bin.y;
@@ -638,7 +691,7 @@ __global__ void __launch_bounds__(kThreads) mvx_voxelize_kernel(const VoxParams 
         for (int ch = P.c_begin; ch < P.c_end; ++ch) {
             for (int item = tid; item < nitems; item += kThreads) {
                 int row = item / lz, x = x0 + (row >> 3), y = y0 + (row & 7), z = z0 + (item - row * lz) * NV;
-                if (x < D && y < D) store_vox(out_mol + (size_t)ch * plane + ((size_t)x * D + y) * D + z, zero);
+                if (x < D && y < D) store_vox<O16>(out_mol + ((size_t)ch * plane + ((size_t)x * D + y) * D + z) * es, zero, P.out_kind);
             }
         }
         return;
@@ -749,7 +802,7 @@ __global__ void __launch_bounds__(kThreads) mvx_voxelize_kernel(const VoxParams 
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     const int ch = c0 + c;
-                    if (ch < P.c_end) store_vox(out_mol + (size_t)ch * plane + ((size_t)x * D + y) * D + z, acc[c]);
+                    if (ch < P.c_end) store_vox<O16>(out_mol + ((size_t)ch * plane + ((size_t)x * D + y) * D + z) * es, acc[c], P.out_kind);
                 }
             }
         }
@@ -784,7 +837,7 @@ constexpr size_t cells_smem_bytes() {
            (MODE == 2 ? (size_t)(2 * NT) * feat_stride<CH>() * sizeof(float) : 0);
 }
 
-template <int MODE, int CH, bool BINARY>
+template <int MODE, int CH, bool BINARY, bool O16>
 __global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cells_kernel(const VoxParams P) {
     constexpr int NT = kThreads, LPR = 4;   // 4 lanes (one float4 each) along z per row: cells of 2 x 4 x 16 voxels
     constexpr int NW = NT / 32;             // warps per CTA
@@ -817,26 +870,14 @@ __global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cell
     const int D = P.dim;
     const int z1 = min(D, z0 + P.tz);
     const size_t plane = (size_t)D * D * D;
-    float* out_mol = P.out + (size_t)mol * P.Cout * plane;
+    constexpr int es = O16 ? 2 : 4;
+    char* out_mol = reinterpret_cast<char*>(P.out) + (size_t)mol * P.Cout * plane * es;
 
     const uint2 bin = P.bins[(size_t)mol * P.ncol + col];
     const int cnt = (int)bin.y;
 
-    if (cnt == 0) {   // empty column: pure zero fill, one address computation per thread item
-        const int lz = (z1 - z0) >> 2;
-        const int nitems = kTile * kTile * lz;
-        const int qstep = NT / lz, rstep = NT - qstep * lz;
-        int row = tid / lz, lzi = tid - row * lz;
-        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int item = tid; item < nitems; item += NT) {
-            const int x = x0 + (row >> 3), y = y0 + (row & 7);
-            if (x < D && y < D) {
-                float* p = out_mol + (size_t)P.c_begin * plane + ((size_t)x * D + y) * D + z0 + lzi * 4;
-                for (int ch = P.c_begin; ch < P.c_end; ++ch, p += plane) __stcs(reinterpret_cast<float4*>(p), zero);
-            }
-            row += qstep; lzi += rstep;
-            if (lzi >= lz) { lzi -= lz; ++row; }
-        }
+    if (cnt == 0) {   // empty column: pure zero fill
+        zero_fill_tile<O16>(out_mol, plane, D, x0, y0, z0, z1, P.c_begin, P.c_end, tid);
         return;
     }
 
@@ -1046,14 +1087,15 @@ __global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cell
                 }
             }
             if (valid) {
-                float* p = out_mol + (size_t)c0 * plane + ((size_t)x * D + y) * D + z;
+                char* p = out_mol + ((size_t)c0 * plane + ((size_t)x * D + y) * D + z) * es;
+                const size_t pstride = plane * es;
                 if (c0 + CH <= P.c_end) {
 #pragma unroll
-                    for (int c = 0; c < CH; ++c, p += plane) store_vox(p, acc[c]);
+                    for (int c = 0; c < CH; ++c, p += pstride) store_vox<O16>(p, acc[c], P.out_kind);
                 } else {
 #pragma unroll
-                    for (int c = 0; c < CH; ++c, p += plane)
-                        if (c0 + c < P.c_end) store_vox(p, acc[c]);
+                    for (int c = 0; c < CH; ++c, p += pstride)
+                        if (c0 + c < P.c_end) store_vox<O16>(p, acc[c], P.out_kind);
                 }
             }
         }
@@ -1083,25 +1125,7 @@ constexpr size_t tiles_smem_bytes() {
            (kThreads / 32) * kWarpList * (2 * sizeof(float4) + sizeof(uint16_t));
 }
 
-__device__ __forceinline__ void zero_fill_tile(float* out_mol, size_t plane, int D, int x0, int y0, int z0, int z1,
-                                               int c_begin, int c_end, int tid) {
-    const int lz = (z1 - z0) >> 2;
-    const int nitems = kTile * kTile * lz;
-    const int qstep = kThreads / lz, rstep = kThreads - qstep * lz;
-    int row = tid / lz, lzi = tid - row * lz;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int item = tid; item < nitems; item += kThreads) {
-        const int x = x0 + (row >> 3), y = y0 + (row & 7);
-        if (x < D && y < D) {
-            float* p = out_mol + (size_t)c_begin * plane + ((size_t)x * D + y) * D + z0 + lzi * 4;
-            for (int ch = c_begin; ch < c_end; ++ch, p += plane) __stcs(reinterpret_cast<float4*>(p), zero);
-        }
-        row += qstep; lzi += rstep;
-        if (lzi >= lz) { lzi -= lz; ++row; }
-    }
-}
-
-template <int MODE, int CH, bool BINARY>
+template <int MODE, int CH, bool BINARY, bool O16>
 __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_tiles_kernel(const VoxParams P) {
     constexpr int LPR = 4, RX = kCellX, RY = kCellY, CZ = kCellZ;
     constexpr int NCY = kTile / RY;
@@ -1124,12 +1148,13 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_tiles_kernel(const V
     const int D = P.dim;
     const int z1 = min(D, z0 + P.tz);
     const size_t plane = (size_t)D * D * D;
-    float* out_mol = P.out + (size_t)mol * P.Cout * plane;
+    constexpr int es = O16 ? 2 : 4;
+    char* out_mol = reinterpret_cast<char*>(P.out) + (size_t)mol * P.Cout * plane * es;
 
     const size_t gcol = (size_t)mol * P.ncol + col;
     const uint2 bin = P.bins[gcol];
     if (bin.y == 0) {   // empty column
-        zero_fill_tile(out_mol, plane, D, x0, y0, z0, z1, P.c_begin, P.c_end, tid);
+        zero_fill_tile<O16>(out_mol, plane, D, x0, y0, z0, z1, P.c_begin, P.c_end, tid);
         return;
     }
     const int ncz_max = (P.tz + CZ - 1) / CZ;
@@ -1139,7 +1164,7 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_tiles_kernel(const V
     const int seg_start = (int)lb_first.x;
     const int total = (int)(lb_last.x + lb_last.y) - seg_start;   // layers of a chunk are consecutive
     if (total == 0) {   // the column has atoms, none reaches this z chunk
-        zero_fill_tile(out_mol, plane, D, x0, y0, z0, z1, P.c_begin, P.c_end, tid);
+        zero_fill_tile<O16>(out_mol, plane, D, x0, y0, z0, z1, P.c_begin, P.c_end, tid);
         return;
     }
     if (tid < ncz) {
@@ -1320,14 +1345,15 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_tiles_kernel(const V
                 }
             }
             if (valid) {
-                float* p = out_mol + (size_t)c0 * plane + ((size_t)x * D + y) * D + z;
+                char* p = out_mol + ((size_t)c0 * plane + ((size_t)x * D + y) * D + z) * es;
+                const size_t pstride = plane * es;
                 if (c0 + CH <= P.c_end) {
 #pragma unroll
-                    for (int c = 0; c < CH; ++c, p += plane) store_vox(p, acc[c]);
+                    for (int c = 0; c < CH; ++c, p += pstride) store_vox<O16>(p, acc[c], P.out_kind);
                 } else {
 #pragma unroll
-                    for (int c = 0; c < CH; ++c, p += plane)
-                        if (c0 + c < P.c_end) store_vox(p, acc[c]);
+                    for (int c = 0; c < CH; ++c, p += pstride)
+                        if (c0 + c < P.c_end) store_vox<O16>(p, acc[c], P.out_kind);
                 }
             }
         }

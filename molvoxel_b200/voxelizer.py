@@ -46,6 +46,7 @@ class Voxelizer:
         density_type: str = "gaussian",
         device: str | torch.device = "cuda",
         blockdim: int | None = None,
+        out_dtype: torch.dtype = torch.float32,
         **kwargs,
     ):
         assert radii_type in self.RADII_TYPE_LIST
@@ -65,6 +66,10 @@ class Voxelizer:
         self.device = torch.device(device)
         if self.device.type == "cuda" and self.device.index is None and torch.cuda.is_available():
             self.device = torch.device("cuda", torch.cuda.current_device())
+        # fp32 is the reference (precision=32).  bfloat16 / float16 grids are computed in fp32 exactly like the
+        # fp32 grid and rounded once on the store: half the bytes of the write-bound op.
+        assert out_dtype in (torch.float32, torch.bfloat16, torch.float16), "out_dtype must be float32, bfloat16 or float16"
+        self.out_dtype = out_dtype
         self._ws = None
         self._pipe = None
         _lib.lib()   # fail loudly here if the CUDA library cannot be built/loaded
@@ -154,7 +159,7 @@ class Voxelizer:
         if batch_size is not None:
             shape = (batch_size,) + shape
         fn = torch.zeros if init_zero else torch.empty
-        return fn(shape, dtype=torch.float32, device=self.device)
+        return fn(shape, dtype=self.out_dtype, device=self.device)
 
     def asarray(self, array, obj: str):
         """torch/voxelizer.py:569-582; coords/center keep fp64 (the numpy oracle's centring precision)."""
@@ -351,8 +356,8 @@ class Voxelizer:
             self._check_radii(mode, radii, N, C)
 
         if out is not None:
-            assert isinstance(out, torch.Tensor) and out.dtype == torch.float32 and out.is_contiguous() and \
-                (out.is_cuda or not have_cuda), "out_grid must be a contiguous float32 CUDA tensor"
+            assert isinstance(out, torch.Tensor) and out.dtype == self.out_dtype and out.is_contiguous() and \
+                (out.is_cuda or not have_cuda), f"out_grid must be a contiguous {self.out_dtype} CUDA tensor"
             if mode == "types":
                 assert out.shape[1] >= C, f"Output channel is less than number of types: {out.shape[1]} < {C}"
                 assert tuple(out.shape[2:]) == (D, D, D), \
@@ -372,7 +377,7 @@ class Voxelizer:
         if not have_cuda:
             raise RuntimeError("molvoxel_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         if out is None:
-            out = torch.empty((B, out_channels, D, D, D), dtype=torch.float32, device=self.device)
+            out = torch.empty((B, out_channels, D, D, D), dtype=self.out_dtype, device=self.device)
 
         # centring stays inside the kernel (fp64 or numpy's fp32-fp32 promotion); the optional random
         # rigid transform is applied to centred coordinates first, like the reference (numpy/voxelizer.py:263-265)
@@ -396,6 +401,7 @@ class Voxelizer:
         b.mode, b.num_mols, b.total_atoms = _lib.MODE[mode], B, N
         b.num_channels, b.out_channels = C, out_channels
         b.radius, b.max_radius = 0.0, 0.0
+        b.out_dtype = _lib.OUT_DTYPE[str(self.out_dtype).replace("torch.", "")]
 
         def fdtype_of(x):
             if isinstance(x, torch.Tensor):

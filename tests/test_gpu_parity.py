@@ -418,3 +418,24 @@ def test_randomized_configs_vs_oracle(seed):
         if mode != "features":
             assert np.array_equal(got != 0, ref != 0)
         assert float(np.abs(got - ref).max()) <= GAUSS_TOL * peak
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("kernel", ["cells", "tiles", "rows"])
+def test_reduced_precision_output_is_the_rounded_fp32_grid(dtype, kernel, monkeypatch):
+    """bf16 / fp16 grids == the fp32 grid rounded once (nearest-even), bit for bit."""
+    monkeypatch.setenv("MVX_KERNEL", kernel)
+    rng = np.random.default_rng(31)
+    offs, coords, types = ligand_batch(rng, 6, 5)
+    feats = rng.uniform(size=(coords.shape[0], 8)).astype(np.float32)
+    for dim in (32, 36):   # 36: z extent not a multiple of 8 -> 8-byte zero-fill stores
+        ref = mv.create_voxelizer(0.5, dim, "scalar", "gaussian", library="b200")
+        low = mv.create_voxelizer(0.5, dim, "scalar", "gaussian", library="b200", out_dtype=dtype)
+        a = ref.forward_types_batch(coords, offs, None, types, 1.0, 5)
+        b = low.forward_types_batch(coords, offs, None, types, 1.0, 5)
+        assert b.dtype == dtype and torch.equal(a.to(dtype), b)
+        a = ref.forward_features_batch(coords, offs, None, feats, 1.0)
+        b = low.forward_features_batch(coords, offs, None, feats, 1.0, out=low.get_empty_grid(8, 6))
+        assert torch.equal(a.to(dtype), b)
+    with pytest.raises(AssertionError):
+        low.forward_types_batch(coords, offs, None, types, 1.0, 5, out=ref.get_empty_grid(5, 6))
