@@ -439,3 +439,21 @@ def test_reduced_precision_output_is_the_rounded_fp32_grid(dtype, kernel, monkey
         assert torch.equal(a.to(dtype), b)
     with pytest.raises(AssertionError):
         low.forward_types_batch(coords, offs, None, types, 1.0, 5, out=ref.get_empty_grid(5, 6))
+
+
+@pytest.mark.parametrize("kernel", ["cells", "tiles"])
+@pytest.mark.parametrize("res", [0.3, 0.4, 0.7])
+def test_resolutions_not_representable_in_fp32(kernel, res, monkeypatch):
+    """Voxel offsets are formed in fp32 inside the kernels; the tolerance band must absorb res != fp32(res)."""
+    monkeypatch.setenv("MVX_KERNEL", kernel)
+    rng = np.random.default_rng(int(res * 100))
+    dim, V = 64, 1500
+    half = res * (dim - 1) / 2
+    coords = rng.uniform(-half, half, size=(V, 3))
+    types = rng.integers(0, 4, size=V)
+    radii = rng.uniform(0.9, 1.9, size=V).astype(np.float32)
+    for density in ("binary", "gaussian"):
+        vox = mv.create_voxelizer(res, dim, "atom-wise", density, library="b200")
+        out = vox.forward_types(coords, np.zeros(3), types, radii).cpu().numpy()
+        ref = OracleVoxelizer(res, dim, "atom-wise", density).forward_types(coords, np.zeros(3), types, radii)
+        _compare(out, ref, density == "binary")
