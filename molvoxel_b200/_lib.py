@@ -12,7 +12,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(CSRC, "libmolvoxel_b200.so")
+SO_PATH = os.environ.get("MVX_SO") or os.path.join(CSRC, "libmolvoxel_b200.so")   # MVX_SO: an experimental build
 SOURCES = [os.path.join(CSRC, "mvx_api.cu")]
 HEADERS = [os.path.join(CSRC, "mvx_kernels.cuh"), os.path.join(os.path.dirname(_HERE), "include", "molvoxel_b200.h")]
 

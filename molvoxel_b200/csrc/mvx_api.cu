@@ -53,7 +53,8 @@ struct Plan {
     int form;        // voxelize kernel form, see enum Form
     int ncell;
     int nlayers, zl, es4;
-    size_t off_lent, off_lmask, off_lbins;
+    size_t off_lent, off_lmask, off_lbins, off_tdesc;
+    int pipe_sc;   // pipelined form: largest tile (entries) it takes
 };
 
 int check_args(const mvx_grid_spec* s, const mvx_batch* b) {
@@ -98,7 +99,11 @@ int pick_chunk(int mode, int nchan);
 //   TILES  entries regrouped per 16-voxel z layer with their feature rows, one flat staging copy,
 //          per-layer warp filter: packed complexes (hundreds of atoms per column)
 //   ROWS   generic lock-step form (any D, scalar stores when D % 4 != 0)
-enum Form { FORM_ROWS = 0, FORM_CELLS = 1, FORM_TILES = 3 };
+//   PIPE   the tile form made persistent: two CTAs per SM walk the tiles, staging is a bulk copy (cp.async.bulk +
+//          mbarrier) issued one tile ahead, no CTA-wide barrier in the steady state: dense batches
+enum Form { FORM_ROWS = 0, FORM_CELLS = 1, FORM_TILES = 3, FORM_PIPE = 4 };
+
+bool layered(int form) { return form == FORM_TILES || form == FORM_PIPE; }
 
 int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     int rc = check_args(s, b);
@@ -153,6 +158,10 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     pl->nzc = (D + 63) / 64;
     int tz = (D + pl->nzc - 1) / pl->nzc;
     tz = (tz + 3) / 4 * 4;
+    if (const char* e = std::getenv("MVX_TZ")) {   // experiments: z extent of a tile (whole 16-voxel layers)
+        const int v = std::atoi(e);
+        if (v >= 16 && v <= 64 && v % 16 == 0 && (D + v - 1) / v * (v / 16) <= 32) tz = v;
+    }
     pl->tz = tz;
     pl->nzc = (D + tz - 1) / tz;
     // tolerance band of the fp32 cutoff test (see DESIGN.md "cutoff decisions")
@@ -182,7 +191,10 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
             if (std::strcmp(e, "rows") == 0) pl->form = FORM_ROWS;
             else if (pl->nv == 4 && std::strcmp(e, "cells") == 0) pl->form = FORM_CELLS;
             else if (pl->nv == 4 && std::strcmp(e, "tiles") == 0) pl->form = FORM_TILES;
+            else if (pl->nv == 4 && std::strcmp(e, "pipe") == 0) pl->form = FORM_PIPE;
         }
+        // channel-wise features patch the staged radii per channel pass, which needs the CTA-synchronous staging
+        if (pl->form == FORM_PIPE && chan_feat) pl->form = FORM_TILES;
     }
     {   // layered entries of the tile kernel
         const int C = b->mode == MVX_MODE_FEATURES ? b->num_channels : 0;
@@ -192,10 +204,12 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
         pl->es4 = 3 + cs / 4;
         pl->nlayers = layers;
         pl->zl = zl;
-        const size_t nle = pl->form == FORM_TILES ? N * (size_t)pl->maxcols * (size_t)zl : 0;
+        const size_t nle = layered(pl->form) ? N * (size_t)pl->maxcols * (size_t)zl : 0;
         pl->off_lent = off;  off += align_up(nle * (size_t)pl->es4 * 16);
         pl->off_lmask = off; off += align_up(nle * sizeof(uint32_t));
-        pl->off_lbins = off; off += align_up(pl->form == FORM_TILES ? B * (size_t)pl->ncol * (size_t)layers * sizeof(uint2) : 0);
+        pl->off_lbins = off; off += align_up(layered(pl->form) ? B * (size_t)pl->ncol * (size_t)layers * sizeof(uint2) : 0);
+        pl->off_tdesc = off; off += align_up(pl->form == FORM_PIPE ? B * (size_t)pl->ncol * (size_t)pl->nzc * sizeof(mvx::TileDesc) : 0);
+        pl->pipe_sc = mvx::kPipeRingQ / 2 / pl->es4;   // the pipelined form takes tiles up to half its ring
     }
     pl->off_entries = off;  off += align_up(pl->form == FORM_CELLS ? N * (size_t)pl->maxcols * sizeof(mvx::ColEntry) : 0);
     pl->total = off;
@@ -207,9 +221,36 @@ cudaError_t set_smem(K kernel, size_t smem) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
+// CTAs of the persistent form: one per SM of the current device
+int pipe_grid(unsigned ntiles, unsigned* grid) {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
+            return -1;
+        sms = n;
+    }
+    const unsigned want = (unsigned)sms;
+    *grid = ntiles < want ? ntiles : want;
+    return 0;
+}
+
 template <int MODE, int CH, bool BINARY, bool O16>
 cudaError_t launch_form_out(const mvx::VoxParams& vp, int form, int nv, unsigned grid, cudaStream_t st) {
-    if (form == FORM_TILES) {
+    if (form == FORM_PIPE) {
+        constexpr size_t smem = mvx::kPipeSmemBytes;
+        static bool cfg = false, cfg_t = false;
+        if (!cfg) { cudaError_t e = set_smem(mvx::mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16>, smem); if (e != cudaSuccess) return e; cfg = true; }
+        unsigned pg = 0;
+        if (pipe_grid(grid, &pg) != 0) return cudaErrorInvalidDevice;
+        mvx::mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16><<<pg, mvx::kPipeThreads, smem, st>>>(vp, grid);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        // tiles with more entries than the pipelined form takes (usually none): a small scanning grid
+        constexpr size_t smem_t = mvx::tiles_smem_bytes<MODE>();
+        if (!cfg_t) { e = set_smem(mvx::mvx_voxelize_sweep_kernel<MODE, CH, BINARY, O16>, smem_t); if (e != cudaSuccess) return e; cfg_t = true; }
+        mvx::mvx_voxelize_sweep_kernel<MODE, CH, BINARY, O16><<<2 * pg < grid ? 2 * pg : grid, mvx::kThreads, smem_t, st>>>(vp, grid);
+    } else if (form == FORM_TILES) {
         constexpr size_t smem = mvx::tiles_smem_bytes<MODE>();
         static bool cfg = false;
         if (!cfg) { cudaError_t e = set_smem(mvx::mvx_voxelize_tiles_kernel<MODE, CH, BINARY, O16>, smem); if (e != cudaSuccess) return e; cfg = true; }
@@ -303,8 +344,8 @@ int mvx_launches_per_call(const mvx_grid_spec* spec, const mvx_batch* batch) {
     const bool chan_feat = batch->mode == MVX_MODE_FEATURES && spec->radii_type == MVX_RADII_CHANNEL_WISE;
     int nvox = chan_feat ? batch->num_channels : 1;
     const int nbin = bin_groups(batch->num_mols, pl.ncol) <= 1 ? 1 : 2;
-    const int nexp = (pl.form != FORM_ROWS && batch->total_atoms > 0) ? 1 : 0;
-    return (batch->total_atoms > 0 ? 1 : 0) + nbin + nexp + nvox;   // prep + bin + expand + voxelize
+    const int nexp = (pl.form != FORM_ROWS && (batch->total_atoms > 0 || pl.form == FORM_PIPE)) ? 1 : 0;
+    return (batch->total_atoms > 0 ? 1 : 0) + nbin + nexp + nvox * (pl.form == FORM_PIPE ? 2 : 1);   // prep + bin + expand + voxelize
 }
 
 int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, void* workspace,
@@ -361,7 +402,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
             mvx::mvx_bin_fill_kernel<<<(unsigned)(B * groups), 256, smem, st>>>(bp, groups);
         }
         MVX_CUDA_OK(cudaGetLastError());
-        if (pl.form != FORM_ROWS && N > 0) {   // column lists -> staged-ready entries
+        if (pl.form != FORM_ROWS && (N > 0 || pl.form == FORM_PIPE)) {   // column lists -> staged-ready entries (+ tile descriptors)
             mvx::ExpandParams ep;
             ep.res = pl.geo.res; ep.half_width = pl.geo.half_width; ep.sigma = spec->sigma;
             ep.tau_lin = pl.tau_lin; ep.tau_quad = pl.tau_quad;
@@ -373,8 +414,9 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
             ep.C = batch->mode == MVX_MODE_FEATURES ? C : 0; ep.features = batch->features;
             ep.lent = (float4*)(ws + pl.off_lent); ep.lmask = (uint32_t*)(ws + pl.off_lmask);
             ep.lbins = (uint2*)(ws + pl.off_lbins);
+            ep.tdesc = pl.form == FORM_PIPE ? (mvx::TileDesc*)(ws + pl.off_tdesc) : nullptr;
             const long long warps = (long long)B * pl.ncol;
-            if (pl.form == FORM_TILES) mvx::mvx_expand_layers_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(ep);
+            if (layered(pl.form)) mvx::mvx_expand_layers_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(ep);
             else mvx::mvx_expand_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(ep);
             MVX_CUDA_OK(cudaGetLastError());
         }
@@ -392,6 +434,8 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         vp.nlayers = pl.nlayers; vp.zl = pl.zl; vp.es4 = pl.es4;
         vp.lent = (const float4*)(ws + pl.off_lent); vp.lmask = (const uint32_t*)(ws + pl.off_lmask);
         vp.lbins = (const uint2*)(ws + pl.off_lbins);
+        vp.tdesc = pl.form == FORM_PIPE ? (const mvx::TileDesc*)(ws + pl.off_tdesc) : nullptr;
+        vp.pipe_sc = pl.pipe_sc;
         const unsigned long long nblk = (unsigned long long)B * pl.ncol * pl.nzc;
         if (nblk > 0x7fffffffULL) return fail(MVX_ERR_BAD_SHAPE, "batch too large for one launch; split it");
         const bool binary = spec->density_type == MVX_DENSITY_BINARY;

@@ -82,6 +82,16 @@ struct __align__(16) ColEntry {
 };
 static_assert(sizeof(ColEntry) == 48, "ColEntry layout");
 
+// One tile (8 x 8 x tz voxels of one molecule) as the pipelined kernel's producer sees it: where its layered
+// entries start, how many there are, and where each 16-voxel z layer ends.  32 bytes, fetched by one bulk copy.
+struct __align__(16) TileDesc {
+    unsigned long long start;   // first layered entry of the tile (index into lent, in entries)
+    uint32_t total;             // entries of the tile (the layers of a z chunk are consecutive)
+    uint32_t lend[4];           // end of layer k relative to start (tz <= 64: at most 4 layers)
+    uint32_t pad;
+};
+static_assert(sizeof(TileDesc) == 32, "TileDesc layout");
+
 // cell shape of the warp-cell kernel: 2 x 4 x 16 voxels (4 lanes of one float4 along z per row)
 constexpr int kCellX = 2, kCellY = 4, kCellZ = 16;
 constexpr int kCellsXY = (kTile / kCellX) * (kTile / kCellY);   // 8 cells per z layer of a tile
@@ -105,6 +115,7 @@ struct ExpandParams {
     float4* lent;       // column with ids [e0, e0 + cnt) owns lent[e0 * zl * es4, (e0 + cnt) * zl * es4)
     uint32_t* lmask;    // per layered entry: 8-bit mask of the layer's cells its cutoff sphere reaches
     uint2* lbins;       // (start relative to the column's layered segment, count) per (molecule, column, layer)
+    TileDesc* tdesc;    // per (molecule, column, z chunk), or nullptr
 };
 
 struct VoxParams {
@@ -127,6 +138,8 @@ struct VoxParams {
     const float4* lent;
     const uint32_t* lmask;
     const uint2* lbins;
+    const TileDesc* tdesc;     // pipelined form; for the tile form: non-null = only tiles with more than pipe_sc entries
+    int pipe_sc;               // pipelined form: largest tile (entries) it takes; larger ones go to the tile form
     void* out;                 // (B, Cout, D, D, D), element type by out_kind
     int out_kind;              // 0 fp32 (reference), 1 bf16, 2 fp16 (reduced-precision output)
 };
@@ -436,7 +449,14 @@ __global__ void __launch_bounds__(256) mvx_expand_layers_kernel(const ExpandPara
     if (gw >= (long long)P.B * P.ncol) return;
     const int mol = (int)(gw / P.ncol), col = (int)(gw % P.ncol);
     const uint2 bin = P.bins[gw];
-    if (bin.y == 0) return;
+    if (bin.y == 0) {
+        if (P.tdesc != nullptr && lane < P.nzc) {
+            TileDesc d;
+            d.start = 0ull; d.total = 0u; d.lend[0] = d.lend[1] = d.lend[2] = d.lend[3] = 0u; d.pad = 0u;
+            P.tdesc[(size_t)gw * P.nzc + lane] = d;
+        }
+        return;
+    }
     const size_t base = (size_t)P.mol_offsets[mol] * (size_t)P.maxcols + bin.x;
     const size_t lbase = base * (size_t)P.zl;
     float4* lent = P.lent + lbase * (size_t)P.es4;
@@ -502,6 +522,23 @@ __global__ void __launch_bounds__(256) mvx_expand_layers_kernel(const ExpandPara
     for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
     const uint32_t my_off = x - my_cnt;
     if (lane < nl) P.lbins[(size_t)gw * nl + lane] = make_uint2(my_off, my_cnt);
+    if (P.tdesc != nullptr) {   // tile descriptors of this column's z chunks (layers of a chunk are consecutive)
+        for (int zc = 0; zc < P.nzc; ++zc) {
+            const int L0 = zc * ncz_max;
+            const int ncz = (min(P.dim, (zc + 1) * P.tz) - zc * P.tz + kCellZ - 1) / kCellZ;
+            const uint32_t o0 = __shfl_sync(0xffffffffu, my_off, L0);
+            uint32_t e[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                e[k] = __shfl_sync(0xffffffffu, my_off + my_cnt, min(L0 + min(k, ncz - 1), 31)) - o0;
+            if (lane == 0) {
+                TileDesc d;
+                d.start = (unsigned long long)lbase + o0; d.total = e[3];
+                d.lend[0] = e[0]; d.lend[1] = e[1]; d.lend[2] = e[2]; d.lend[3] = e[3]; d.pad = 0u;
+                P.tdesc[(size_t)gw * P.nzc + zc] = d;
+            }
+        }
+    }
 
     for (int L = 0; L < nl; ++L) {
         uint32_t pos = __shfl_sync(0xffffffffu, my_off, L);
@@ -522,10 +559,15 @@ __global__ void __launch_bounds__(256) mvx_expand_layers_kernel(const ExpandPara
                 const double rs = (double)r * P.sigma;
                 const float kc = (float)(-0.5 * 1.4426950408889634 / (rs * rs));
                 const float ax = (float)(rec.px - ox0), ay = (float)(rec.py - oy0), az = (float)(rec.pz + P.half_width);
+                // forbidden planes (block-cull emulation) are kept only where the cutoff sphere can reach them, so
+                // that most entries carry "none" and the voxelize kernels skip the cull arithmetic
                 const int fx = rec.fx - x0, fy = rec.fy - y0;
-                const uint32_t forb = (uint32_t)((rec.fx >= 0 && fx >= 0 && fx < kTile) ? fx : 0xFF) |
-                                      ((uint32_t)((rec.fy >= 0 && fy >= 0 && fy < kTile) ? fy : 0xFF) << 8) |
-                                      ((uint32_t)(rec.fz >= 0 ? rec.fz : 0xFFFF) << 16);
+                const float rr = r * 1.001f + 0.01f * resf;
+                const bool kx = rec.fx >= 0 && fx >= 0 && fx < kTile && fabsf(ax - fx * resf) <= rr;
+                const bool ky = rec.fy >= 0 && fy >= 0 && fy < kTile && fabsf(ay - fy * resf) <= rr;
+                const bool kz = rec.fz >= 0 && fabsf(az - rec.fz * resf) <= rr;
+                const uint32_t forb = (uint32_t)(kx ? fx : 0xFF) | ((uint32_t)(ky ? fy : 0xFF) << 8) |
+                                      ((uint32_t)(kz ? rec.fz : 0xFFFF) << 16);
                 // cells of this layer reached by the cutoff sphere: exact sphere / voxel-centre-box test
                 const float lim = r2hi + 1e-4f * (1.f + r2hi);
                 const float ez2 = layer_ez2(az, lo, hi);
@@ -544,7 +586,7 @@ __global__ void __launch_bounds__(256) mvx_expand_layers_kernel(const ExpandPara
                 e[0] = make_float4(ax, ay, az, r2hi);
                 e[1] = make_float4(r2lo, kc, __uint_as_float(forb),
                                    P.mode == 1 ? __uint_as_float((uint32_t)P.types[n]) : r);
-                e[2] = make_float4(__uint_as_float(n), 0.f, 0.f, 0.f);
+                e[2] = make_float4(__uint_as_float(n), __uint_as_float(cm), 0.f, 0.f);
                 lmask[slot] = cm;
                 if (P.mode == 2) {
                     const float* f = P.features + (size_t)n * P.C;
@@ -628,15 +670,15 @@ __device__ __forceinline__ void store_vox(char* p, const float (&v)[1], int kind
 
 // Division-free zero fill of one tile (8 x 8 x [z0, z1) voxels, channels [c_begin, c_end)), 16-byte stores.
 // VPI voxels of ES bytes per thread item; the fp32 instance (4 x 4 B) is the hot path of ligand batches.
-template <int VPI, int ES>
+template <int VPI, int ES, int NT>
 __device__ __forceinline__ void zero_fill_items(char* out_mol, size_t plane, int D, int x0, int y0, int z0, int z1,
                                                 int c_begin, int c_end, int tid) {
     const int lz = (z1 - z0) / VPI;
     const int nitems = kTile * kTile * lz;
-    const int qstep = kThreads / lz, rstep = kThreads - qstep * lz;
+    const int qstep = NT / lz, rstep = NT - qstep * lz;
     int row = tid / lz, lzi = tid - row * lz;
     const size_t pstride = plane * ES;
-    for (int item = tid; item < nitems; item += kThreads) {
+    for (int item = tid; item < nitems; item += NT) {
         const int x = x0 + (row >> 3), y = y0 + (row & 7);
         if (x < D && y < D) {
             char* p = out_mol + ((size_t)c_begin * plane + ((size_t)x * D + y) * D + z0 + lzi * VPI) * ES;
@@ -651,12 +693,12 @@ __device__ __forceinline__ void zero_fill_items(char* out_mol, size_t plane, int
     }
 }
 
-template <bool O16>
+template <bool O16, int NT = kThreads>
 __device__ __forceinline__ void zero_fill_tile(char* out_mol, size_t plane, int D, int x0, int y0, int z0, int z1,
                                                int c_begin, int c_end, int tid) {
-    if (!O16) zero_fill_items<4, 4>(out_mol, plane, D, x0, y0, z0, z1, c_begin, c_end, tid);
-    else if (((z1 - z0) & 7) == 0 && (D & 7) == 0) zero_fill_items<8, 2>(out_mol, plane, D, x0, y0, z0, z1, c_begin, c_end, tid);
-    else zero_fill_items<4, 2>(out_mol, plane, D, x0, y0, z0, z1, c_begin, c_end, tid);
+    if (!O16) zero_fill_items<4, 4, NT>(out_mol, plane, D, x0, y0, z0, z1, c_begin, c_end, tid);
+    else if (((z1 - z0) & 7) == 0 && (D & 7) == 0) zero_fill_items<8, 2, NT>(out_mol, plane, D, x0, y0, z0, z1, c_begin, c_end, tid);
+    else zero_fill_items<4, 2, NT>(out_mol, plane, D, x0, y0, z0, z1, c_begin, c_end, tid);
 }
 
 template <int MODE, int CH, bool BINARY, int NV, bool O16>
@@ -1126,7 +1168,7 @@ constexpr size_t tiles_smem_bytes() {
 }
 
 template <int MODE, int CH, bool BINARY, bool O16>
-__global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_tiles_kernel(const VoxParams P) {
+__device__ __forceinline__ void tiles_body(const VoxParams& P, const int tile_id) {
     constexpr int LPR = 4, RX = kCellX, RY = kCellY, CZ = kCellZ;
     constexpr int NCY = kTile / RY;
     constexpr int NW = kThreads / 32;
@@ -1140,7 +1182,7 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_tiles_kernel(const V
     uint16_t* wI_all = reinterpret_cast<uint16_t*>(wB_all + NW * kWarpList);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int t = blockIdx.x;
+    int t = tile_id;
     const int zc = t % P.nzc; t /= P.nzc;
     const int col = t % P.ncol;
     const int mol = t / P.ncol;
@@ -1357,6 +1399,404 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_tiles_kernel(const V
                 }
             }
         }
+    }
+}
+
+template <int MODE, int CH, bool BINARY, bool O16>
+__global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_tiles_kernel(const VoxParams P) {
+    tiles_body<MODE, CH, BINARY, O16>(P, (int)blockIdx.x);
+}
+
+// Companion of the pipelined form: a small grid scans the tile descriptors and does, with the tile form's
+// multi-round staging, the few tiles that have more entries than the pipelined form takes (usually none).
+constexpr int kSweepList = 64;
+template <int MODE, int CH, bool BINARY, bool O16>
+__global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_sweep_kernel(const VoxParams P, const unsigned ntiles) {
+    __shared__ int s_list[kSweepList];
+    __shared__ int s_n;
+    const unsigned chunk = (ntiles + gridDim.x - 1) / gridDim.x;
+    const unsigned t0 = blockIdx.x * chunk, t1 = min(ntiles, t0 + chunk);
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (unsigned t = t0 + threadIdx.x; t < t1; t += kThreads) {
+        if (P.tdesc[t].total > (uint32_t)P.pipe_sc) {
+            const int i = atomicAdd(&s_n, 1);
+            if (i < kSweepList) s_list[i] = (int)t;
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n == 0) return;
+    if (n <= kSweepList) {
+        for (int i = 0; i < n; ++i) {
+            tiles_body<MODE, CH, BINARY, O16>(P, s_list[i]);
+            __syncthreads();
+        }
+    } else {   // more overflow tiles than the list holds: walk the chunk
+        for (unsigned t = t0; t < t1; ++t) {
+            if (P.tdesc[t].total > (uint32_t)P.pipe_sc) {
+                tiles_body<MODE, CH, BINARY, O16>(P, (int)t);
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// voxelize, "pipelined" form (dense batches; needs D % 4 == 0).  Same tile, cell and lane layout and the same
+// arithmetic as the tile form, but with ONE PERSISTENT CTA PER SM (12 warps, up to 168 registers: no spills) that
+// walks the tiles round-robin, and a tile's staging is an asynchronous bulk copy (cp.async.bulk, completion on
+// an mbarrier) issued several tiles ahead by thread 0 into a shared-memory RING allocated by bytes:
+//   descriptor of tile k+1 (32 B)  ->  layered entries of tile k (one contiguous block)  ->  compute.
+// There is no CTA-wide barrier in the steady state.  The work items of a tile (cell x channel chunk) are handed
+// out dynamically (a shared-memory counter per slot), and the warps drift apart by up to the ring depth: a warp waits on
+// the "full" mbarrier of its tile's slot, draws cells until none is left, arrives on the slot's "empty" mbarrier
+// and moves on.  The global-memory latency of staging is hidden behind earlier tiles and the warps no longer
+// reach their store bursts together.  Thread 0 polls (never blocks on) the "empty" barriers between its cells.
+// Tiles with more entries than half the ring are skipped here and done by the tile form (second launch,
+// which exits at once everywhere else).
+// ---------------------------------------------------------------------------------------------
+#ifndef MVX_PIPE_THREADS
+#define MVX_PIPE_THREADS 384
+#endif
+constexpr int kPipeThreads = MVX_PIPE_THREADS;   // 12 warps: 168 registers per thread, no spills
+constexpr int kPipeWarps = kPipeThreads / 32;
+constexpr int kPipeSlots = 8;    // tiles in flight (descriptor + barrier slots)
+constexpr int kPipeSmemBytes = 232448;   // 227 KB: the whole SM
+constexpr int kPipeFixedBytes = kPipeSlots * ((int)sizeof(TileDesc) + 3 * 8 + 2 * 4) +
+                                kPipeWarps * kWarpList * ((int)sizeof(float4) + (int)sizeof(uint16_t));
+constexpr int kPipeRingQ = (kPipeSmemBytes - kPipeFixedBytes) / 16;   // float4 words of the entry ring
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {   // may suspend up to ~20 us
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+    return ok != 0u;
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0u;
+}
+// Bounded wait: a pipeline bug traps (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 16)) __trap();
+    }
+}
+// global -> shared bulk copy (bytes % 16 == 0, both addresses 16-byte aligned); completion counts on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int MODE, int CH, bool BINARY, bool O16>
+__global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(const VoxParams P, const unsigned ntiles) {
+    constexpr int LPR = 4, RX = kCellX, RY = kCellY, CZ = kCellZ;
+    constexpr int NCY = kTile / RY;
+    constexpr int NW = kPipeWarps;
+    constexpr int ND = kPipeSlots;
+    constexpr int Q = kPipeRingQ;
+
+    extern __shared__ __align__(128) float4 smem_q[];
+    float4* const ring = smem_q;
+    TileDesc* const sDesc = reinterpret_cast<TileDesc*>(smem_q + Q);
+    uint64_t* const full = reinterpret_cast<uint64_t*>(sDesc + ND);   // slot s: the tile's entries have landed
+    uint64_t* const empty = full + ND;                                 // slot s: all warps are done with the tile
+    uint64_t* const dfull = empty + ND;                                // slot s: the descriptor has landed
+    int* const sOff = reinterpret_cast<int*>(dfull + ND);              // slot s: ring offset of the tile's entries
+    int* const sNext = sOff + ND;                                      // slot s: next work item (cell x channel chunk) to hand out
+    float4* const wA_all = reinterpret_cast<float4*>(sNext + ND);
+    uint16_t* const wI_all = reinterpret_cast<uint16_t*>(wA_all + NW * kWarpList);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int D = P.dim;
+    const size_t plane = (size_t)D * D * D;
+    constexpr int es = O16 ? 2 : 4;
+    const int ES4 = P.es4;
+    const uint32_t SC = (uint32_t)P.pipe_sc;   // largest tile (entries) this form takes
+    const unsigned G = gridDim.x;
+
+    float4* const wA = wA_all + warp * kWarpList;
+    uint16_t* const wI = wI_all + warp * kWarpList;
+
+    const float resf = (float)P.res;
+    const float inv_res = 1.0f / resf;
+    const int row = lane / LPR, zq = lane % LPR;
+    const int rx = row / RY, ry = row % RY;
+
+    // ---- producer (thread 0) -------------------------------------------------------------------
+    unsigned next_k = 0;   // first iteration whose entries have not been requested yet
+    unsigned rel_k = 0;    // oldest iteration not yet seen released (its slot and ring bytes are still in use)
+    int head = 0;          // ring position (float4 words) of the next allocation
+    auto issue_desc = [&](unsigned k) {   // descriptor of iteration k's tile -> slot k % ND
+        const unsigned t = blockIdx.x + k * G;
+        if (t < ntiles) {
+            const int s = (int)(k & (ND - 1));
+            mbar_arrive_expect_tx(&dfull[s], (uint32_t)sizeof(TileDesc));
+            bulk_g2s(&sDesc[s], P.tdesc + t, (uint32_t)sizeof(TileDesc), &dfull[s]);
+        }
+    };
+    // Requests the entries of iteration next_k (and the descriptor after it) if a slot and ring space are free.
+    auto produce = [&](bool block) -> bool {
+        const unsigned k = next_k;
+        if (blockIdx.x + k * G >= ntiles) return false;
+        const int s = (int)(k & (ND - 1));
+        auto release_oldest = [&]() -> bool {   // wait for / poll the release of the oldest tile in flight
+            uint64_t* const eb = &empty[rel_k & (ND - 1)];
+            const uint32_t epar = (rel_k / ND) & 1u;
+            if (block) mbar_wait(eb, epar);
+            else if (!mbar_test(eb, epar)) return false;
+            ++rel_k;
+            return true;
+        };
+        // slots: iteration k + 1's descriptor goes to slot (k + 1) % ND, so at most ND - 2 tiles stay in flight
+        while (next_k - rel_k > (unsigned)(ND - 2))
+            if (!release_oldest()) return false;
+        mbar_wait(&dfull[s], (k / ND) & 1u);   // requested when iteration k - 1 was produced
+        const unsigned long long start = sDesc[s].start;
+        const uint32_t total = sDesc[s].total;
+        const int need = (total > 0u && total <= SC) ? (int)total * ES4 : 0;
+        int at;
+        for (;;) {
+            if (next_k == rel_k) { at = 0; break; }            // nothing in flight: restart at the ring's base
+            if (need == 0) { at = head; break; }
+            const int tail = sOff[rel_k & (ND - 1)];
+            if (head >= tail) {
+                if (need <= Q - head) { at = head; break; }
+                if (need < tail) { at = 0; break; }
+            } else if (need < tail - head) { at = head; break; }
+            if (!release_oldest()) return false;
+        }
+        sOff[s] = at;
+        sNext[s] = 0;
+        if (need > 0) {
+            const uint32_t bytes = (uint32_t)need * (uint32_t)sizeof(float4);
+            mbar_arrive_expect_tx(&full[s], bytes);
+            bulk_g2s(ring + at, P.lent + start * (unsigned long long)ES4, bytes, &full[s]);
+        } else {
+            mbar_arrive(&full[s]);   // nothing to stage: empty tile, or an overflow tile left to the tile form
+        }
+        head = at + need;
+        issue_desc(k + 1);
+        next_k = k + 1;
+        return true;
+    };
+
+    if (tid == 0) {
+        for (int i = 0; i < ND; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NW); mbar_init(&dfull[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) issue_desc(0);
+
+    unsigned it = 0;
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
+        if (tid == 0) {
+            while (next_k <= it) produce(true);
+            while (produce(false)) {}
+        }
+        __syncwarp();
+        const int s = (int)(it & (ND - 1));
+        mbar_wait(&dfull[s], (it / ND) & 1u);
+        const uint32_t total = sDesc[s].total;
+
+        if (total != 0u && total <= SC) {
+            unsigned t = tile;
+            const int zc = (int)(t % (unsigned)P.nzc); t /= (unsigned)P.nzc;
+            const int col = (int)(t % (unsigned)P.ncol);
+            const int mol = (int)(t / (unsigned)P.ncol);
+            const int x0 = (col / P.ncx) * kTile, y0 = (col % P.ncx) * kTile, z0 = zc * P.tz;
+            const int z1 = min(D, z0 + P.tz);
+            char* const out_mol = reinterpret_cast<char*>(P.out) + (size_t)mol * P.Cout * plane * es;
+            const int ncells = kCellsXY * ((z1 - z0 + CZ - 1) / CZ);
+            const int nitems = ncells * ((P.c_end - P.c_begin + CH - 1) / CH);
+            mbar_wait(&full[s], (it / ND) & 1u);
+            const int sb = sOff[s];   // this tile's entries: ring[sb + i * ES4 + {0, 1, 2, 3..}]
+            {
+                {
+                    // work items (cell x channel chunk) are handed out dynamically: the producer warp and warps that
+                    // drew heavy cells simply take fewer
+                    for (;;) {
+                        int item = 0;
+                        if (lane == 0) item = atomicAdd(&sNext[s], 1);
+                        item = __shfl_sync(0xffffffffu, item, 0);
+                        if (item >= nitems) break;
+                        const int chunk = item / ncells, cell = item - chunk * ncells;
+                        const int c0 = P.c_begin + chunk * CH;
+                        const int cz = cell / kCellsXY, cxy = cell % kCellsXY;
+                        const int cxl = cxy / NCY, cyl = cxy % NCY;
+                        const int lx = cxl * RX + rx, ly = cyl * RY + ry, lzv = cz * CZ + zq * 4;
+                        const int x = x0 + lx, y = y0 + ly, z = z0 + lzv;
+                        const bool valid = x < D && y < D && z < z1;
+                        const uint32_t lane_key = (uint32_t)lx | ((uint32_t)ly << 8);
+                        const float ox = (float)lx * resf, oy = (float)ly * resf;
+                        float oz[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) oz[k] = (float)(z + k) * resf;   // grid-absolute, like the entries' z
+
+                        float acc[CH][4];
+#pragma unroll
+                        for (int c = 0; c < CH; ++c)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) acc[c][k] = 0.f;
+
+                        int base = cz > 0 ? (int)sDesc[s].lend[cz - 1] : 0;
+                        const int end = (int)sDesc[s].lend[cz];
+                        while (base < end) {
+                            // 1. warp filter over this cell's layer: atoms whose mask names the cell, order kept
+                            int wn = 0;
+                            while (base < end && wn <= kWarpList - 32) {
+                                const int i = base + lane;
+                                const bool in = (i < end) && ((__float_as_uint(ring[sb + i * ES4 + 2].y) >> cxy) & 1u);
+                                const uint32_t m = __ballot_sync(0xffffffffu, in);
+                                if (in) {
+                                    const int pos = wn + __popc(m & ((1u << lane) - 1u));
+                                    wA[pos] = ring[sb + i * ES4]; wI[pos] = (uint16_t)i;
+                                }
+                                wn += __popc(m);
+                                base += 32;
+                            }
+                            __syncwarp();
+                            // 2. every lane tests the warp list against the nearest of its 4 voxels -> hit bitmasks
+                            uint32_t mask_lo = 0u, mask_hi = 0u;
+                            if (valid) {
+                                auto near_hit = [&](const float4 A) -> bool {
+                                    const float dx = A.x - ox, dy = A.y - oy;
+                                    const float tz_ = A.z - oz[0];
+                                    const float dzc = fmaf(-resf, fminf(fmaxf(rintf(tz_ * inv_res), 0.f), 3.f), tz_);
+                                    return fmaf(dzc, dzc, fmaf(dx, dx, dy * dy)) <= A.w;
+                                };
+                                const int n_lo = min(wn, 32);
+#pragma unroll 4
+                                for (int j = 0; j < n_lo; ++j)
+                                    if (near_hit(wA[j])) mask_lo |= 1u << j;
+#pragma unroll 4
+                                for (int j = 32; j < wn; ++j)
+                                    if (near_hit(wA[j])) mask_hi |= 1u << (j - 32);
+                            }
+                            // 3. lane-private walk over the set bits, ascending (fixed fp32 summation order)
+                            while (__any_sync(0xffffffffu, (mask_lo | mask_hi) != 0u)) {
+                                if ((mask_lo | mask_hi) != 0u) {
+                                    int j;
+                                    if (mask_lo != 0u) { j = __ffs((int)mask_lo) - 1; mask_lo &= mask_lo - 1u; }
+                                    else { j = 31 + __ffs((int)mask_hi); mask_hi &= mask_hi - 1u; }
+                                    const int eb = sb + (int)wI[j] * ES4;   // this atom's staged entry
+                                    const float4 A = wA[j];
+                                    const float4 Bv = ring[eb + 1];
+                                    const float dx = A.x - ox, dy = A.y - oy;
+                                    const float dxy = fmaf(dx, dx, dy * dy);
+                                    // |s - r^2| <= tau (slightly widened) for any of the 4 voxels -> replay in fp64
+                                    const float r2c = 0.5f * (A.w + Bv.x), tauh = 0.5f * (A.w - Bv.x) * 1.0001f + 1e-12f;
+                                    float sk[4], w[4], dmin = 3.0e38f;
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const float dz = A.z - oz[k];
+                                        sk[k] = fmaf(dz, dz, dxy);
+                                        w[k] = (sk[k] < Bv.x) ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
+                                        dmin = fminf(dmin, fabsf(sk[k] - r2c));
+                                    }
+                                    const uint32_t forb = __float_as_uint(Bv.z);
+                                    if (dmin <= tauh || forb != kNoForb) {   // rare: tolerance band, or a block-cull plane in reach
+                                        bool off[4];
+                                        {   // block-cull emulation: voxels on the atom's forbidden planes take nothing from it
+                                            const uint32_t tx = forb ^ lane_key;
+                                            const bool row_off = (tx & 0xFFu) == 0u || (tx & 0xFF00u) == 0u;
+                                            const int dzf = (int)(forb >> 16) - z;
+#pragma unroll
+                                            for (int k = 0; k < 4; ++k) off[k] = row_off || dzf == k;
+                                        }
+                                        if (dmin <= tauh) {
+                                            const int n = (int)__float_as_uint(ring[eb + 2].x);
+                                            const float r32 = (MODE == 1) ? P.recs[n].r : Bv.w;
+#pragma unroll
+                                            for (int k = 0; k < 4; ++k) {
+                                                if (sk[k] >= Bv.x && !off[k]) {
+                                                    const bool hit = sk[k] <= A.w && exact_hit(P.recs + n, r32, x, y, z + k, P.res, P.half_width);
+                                                    w[k] = hit ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
+                                                }
+                                            }
+                                        }
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) w[k] = off[k] ? 0.f : w[k];
+                                    }
+                                    if (MODE == 0) {
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) acc[0][k] += w[k];
+                                    } else if (MODE == 1) {
+                                        const int ct = __float_as_int(Bv.w) - c0;
+#pragma unroll
+                                        for (int c = 0; c < CH; ++c)
+#pragma unroll
+                                            for (int k = 0; k < 4; ++k) acc[c][k] += (ct == c) ? w[k] : 0.f;
+                                    } else if (CH >= 4) {
+                                        const int fb = eb + 3 + (c0 >> 2);
+#pragma unroll
+                                        for (int c4 = 0; c4 < CH; c4 += 4) {
+                                            const float4 fv = ring[fb + (c4 >> 2)];
+                                            const float f[4] = {fv.x, fv.y, fv.z, fv.w};
+#pragma unroll
+                                            for (int k = 0; k < 4; ++k) {   // channel pairs through the packed FMA
+                                                ffma2(acc[c4][k], acc[c4 + 1][k], f[0], f[1], w[k]);
+                                                ffma2(acc[c4 + 2][k], acc[c4 + 3][k], f[2], f[3], w[k]);
+                                            }
+                                        }
+                                    } else {
+                                        const float f = reinterpret_cast<const float*>(ring + eb + 3)[c0];
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) acc[0][k] = fmaf(f, w[k], acc[0][k]);
+                                    }
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        if (valid) {
+                            char* p = out_mol + ((size_t)c0 * plane + ((size_t)x * D + y) * D + z) * es;
+                            const size_t pstride = plane * es;
+                            if (c0 + CH <= P.c_end) {
+#pragma unroll
+                                for (int c = 0; c < CH; ++c, p += pstride) store_vox<O16>(p, acc[c], P.out_kind);
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < CH; ++c, p += pstride)
+                                    if (c0 + c < P.c_end) store_vox<O16>(p, acc[c], P.out_kind);
+                            }
+                        }
+                        if (tid == 0) produce(false);   // keep the ring topped up without ever blocking
+                    }
+                }
+            }
+        } else if (total == 0u) {
+            unsigned t = tile;
+            const int zc = (int)(t % (unsigned)P.nzc); t /= (unsigned)P.nzc;
+            const int col = (int)(t % (unsigned)P.ncol);
+            const int mol = (int)(t / (unsigned)P.ncol);
+            const int z0 = zc * P.tz;
+            zero_fill_tile<O16, kPipeThreads>(reinterpret_cast<char*>(P.out) + (size_t)mol * P.Cout * plane * es, plane, D,
+                                              (col / P.ncx) * kTile, (col % P.ncx) * kTile, z0, min(D, z0 + P.tz),
+                                              P.c_begin, P.c_end, tid);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
     }
 }
 

@@ -238,7 +238,7 @@ def test_dense_cluster_overflows_staging_and_warp_lists(mode):
         assert np.array_equal(out, ovox.forward_features(coords, None, feats, 1.0))
 
 
-@pytest.mark.parametrize("kernel", ["rows", "cells", "tiles"])
+@pytest.mark.parametrize("kernel", ["rows", "cells", "tiles", "pipe"])
 def test_kernel_variants_agree_bitwise(kernel, monkeypatch):
     """Every kernel form gives the same bits (binary) on a mixed batch."""
     monkeypatch.setenv("MVX_KERNEL", kernel)
@@ -338,7 +338,7 @@ def test_odd_shapes_vs_oracle(dim, res, mode, C, radii_type, rmax, V, density, b
     _compare(out.cpu().numpy(), ref, density == "binary")
 
 
-@pytest.mark.parametrize("kernel", ["cells", "tiles", "rows"])
+@pytest.mark.parametrize("kernel", ["cells", "tiles", "pipe", "rows"])
 def test_no_out_of_bounds_global_writes(kernel, monkeypatch):
     """compute-sanitizer is closed on this GPU pool, so: sentinel guard bands around the output grid and the
     workspace must survive a call untouched (catches stray global writes of any kernel)."""
@@ -421,7 +421,7 @@ def test_randomized_configs_vs_oracle(seed):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("kernel", ["cells", "tiles", "rows"])
+@pytest.mark.parametrize("kernel", ["cells", "tiles", "pipe", "rows"])
 def test_reduced_precision_output_is_the_rounded_fp32_grid(dtype, kernel, monkeypatch):
     """bf16 / fp16 grids == the fp32 grid rounded once (nearest-even), bit for bit."""
     monkeypatch.setenv("MVX_KERNEL", kernel)
@@ -441,7 +441,7 @@ def test_reduced_precision_output_is_the_rounded_fp32_grid(dtype, kernel, monkey
         low.forward_types_batch(coords, offs, None, types, 1.0, 5, out=ref.get_empty_grid(5, 6))
 
 
-@pytest.mark.parametrize("kernel", ["cells", "tiles"])
+@pytest.mark.parametrize("kernel", ["cells", "tiles", "pipe"])
 @pytest.mark.parametrize("res", [0.3, 0.4, 0.7])
 def test_resolutions_not_representable_in_fp32(kernel, res, monkeypatch):
     """Voxel offsets are formed in fp32 inside the kernels; the tolerance band must absorb res != fp32(res)."""
@@ -457,3 +457,65 @@ def test_resolutions_not_representable_in_fp32(kernel, res, monkeypatch):
         out = vox.forward_types(coords, np.zeros(3), types, radii).cpu().numpy()
         ref = OracleVoxelizer(res, dim, "atom-wise", density).forward_types(coords, np.zeros(3), types, radii)
         _compare(out, ref, density == "binary")
+
+
+PIPE_CASES = [
+    # name, dim, res, mode, C, radii_type, V per molecule, B, density
+    ("pocket48_feat16", 48, 0.5, "features", 16, "scalar", 2000, 12, "gaussian"),    # 432 tiles > 296 CTAs: several tiles per CTA
+    ("complex96_feat32", 96, 0.375, "features", 32, "atom-wise", 6000, 3, "gaussian"),  # two z chunks, two channel passes
+    ("types9_64", 64, 0.5, "types", 9, "scalar", 1500, 6, "binary"),
+    ("single_52", 52, 0.5, "single", 1, "atom-wise", 900, 5, "gaussian"),              # layers 16,16,16,4
+]
+
+
+@pytest.mark.parametrize("name,dim,res,mode,C,radii_type,V,B,density", PIPE_CASES, ids=[c[0] for c in PIPE_CASES])
+def test_pipelined_form_equals_tile_form_bitwise(name, dim, res, mode, C, radii_type, V, B, density, monkeypatch):
+    """The persistent bulk-copy/mbarrier kernel runs the tile form's arithmetic: identical bits, Gaussian included,
+    with several tiles per CTA, ragged and empty molecules."""
+    rng = np.random.default_rng(len(name) * 7 + dim)
+    counts = rng.integers(V // 2, V + 1, size=B)
+    counts[B // 2] = 0
+    offs = np.zeros(B + 1, dtype=np.int32)
+    offs[1:] = np.cumsum(counts)
+    N = int(offs[-1])
+    half = res * (dim - 1) / 2
+    coords = rng.uniform(-half - 1, half + 1, size=(N, 3))
+    radii = 1.25 if radii_type == "scalar" else rng.uniform(1.0, 2.0, size=N).astype(np.float32)
+    types = rng.integers(0, C, size=N).astype(np.int32)
+    feats = rng.uniform(-1, 1, size=(N, C)).astype(np.float32)
+    outs = {}
+    for kernel in ("tiles", "pipe"):
+        monkeypatch.setenv("MVX_KERNEL", kernel)
+        vox = mv.create_voxelizer(res, dim, radii_type, density, library="b200")
+        if mode == "types":
+            outs[kernel] = vox.forward_types_batch(coords, offs, None, types, radii, C)
+        elif mode == "features":
+            outs[kernel] = vox.forward_features_batch(coords, offs, None, feats, radii)
+        else:
+            outs[kernel] = vox.forward_single_batch(coords, offs, None, radii)
+        vox.check_status()
+    assert torch.equal(outs["tiles"], outs["pipe"])
+    assert float(outs["pipe"][B // 2].abs().max()) == 0.0
+
+
+def test_pipelined_form_overflow_tiles_vs_oracle(monkeypatch):
+    """More entries in a tile than one stage buffer holds: the synchronous multi-round path inside the
+    persistent loop, next to ordinary prefetched tiles, against the oracle (binary, bit-exact)."""
+    monkeypatch.setenv("MVX_KERNEL", "pipe")
+    rng = np.random.default_rng(123)
+    B = 3
+    coords, offs = [], [0]
+    for m in range(B):
+        c = np.concatenate([rng.normal(scale=0.7, size=(1500, 3)) + rng.uniform(-4, 4, size=3),
+                            rng.uniform(-9.5, 9.5, size=(700, 3))])
+        rng.shuffle(c)
+        coords.append(c)
+        offs.append(offs[-1] + len(c))
+    coords = np.concatenate(coords)
+    offs = np.asarray(offs, dtype=np.int32)
+    feats = rng.integers(0, 4, size=(len(coords), 20)).astype(np.float32)   # small integers: sums exact in fp32
+    vox = mv.create_voxelizer(0.5, 40, "scalar", "binary", library="b200")
+    out = vox.forward_features_batch(coords, offs, None, feats, 1.0).cpu().numpy()
+    ref = oracle_forward_batch(0.5, 40, "scalar", "binary", 0.5, 8, "features", offs, coords, None, None, feats, 20, 1.0,
+                               num_threads=8)
+    assert np.array_equal(out, ref)
