@@ -39,17 +39,23 @@ WORKLOADS = {
 }
 
 
+ATOMS_OVERRIDE = 0
+
+
 def make_batch(name: str, B: int, seed: int):
     """Seeded synthetic inputs of SURVEY.md §8d (coordinates rounded to fp32-representable values)."""
     w = WORKLOADS[name]
     rng = np.random.default_rng(seed)
     lo, hi = w["atoms"]
+    uniform_cube = lo >= 1000   # pocket / complex workloads; ligands are random walks
+    if ATOMS_OVERRIDE:          # density sweeps (--atoms): same distribution, another atom count
+        lo = hi = ATOMS_OVERRIDE
     counts = rng.integers(lo, hi + 1, size=B)
     offs = np.zeros(B + 1, dtype=np.int32)
     offs[1:] = np.cumsum(counts)
     N = int(offs[-1])
     mol_of = np.repeat(np.arange(B), counts)
-    if lo < 1000:   # ligand: 3-D random walk with 1.5 A steps, recentred
+    if not uniform_cube:   # ligand: 3-D random walk with 1.5 A steps, recentred
         d = rng.normal(size=(N, 3))
         d /= np.linalg.norm(d, axis=1, keepdims=True)
         d *= 1.5
@@ -484,10 +490,13 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--atoms", type=int, default=0, help="atoms per molecule (density sweeps; default: the workload's own)")
     ap.add_argument("--out-dtype", default="float32", choices=["float32", "bfloat16", "float16"],
                     help="reduced-precision output grids (not the headline metric, which is fp32)")
     ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    global ATOMS_OVERRIDE
+    ATOMS_OVERRIDE = max(0, args.atoms)
     if args.steps <= 0:
         args.steps = {"cfg4": 200, "cfg3": 300, "cfg2": 300, "cfg5": 100}[args.workload] if args.impl == "b200" else 5
     if args.cpu_baseline_worker:

@@ -186,7 +186,7 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     {
         const double cols_per_atom = std::pow(2.0 * reach / (mvx::kTile * s->resolution) + 1.0, 2.0);
         const double per_col = (B > 0) ? (double)N * cols_per_atom / ((double)B * pl->ncol) : 0.0;
-        pl->form = pl->nv != 4 ? FORM_ROWS : (per_col >= 200.0 ? FORM_TILES : FORM_CELLS);
+        pl->form = pl->nv != 4 ? FORM_ROWS : (per_col >= 64.0 ? FORM_PIPE : FORM_CELLS);
         if (const char* e = std::getenv("MVX_KERNEL")) {   // experiments / tests
             if (std::strcmp(e, "rows") == 0) pl->form = FORM_ROWS;
             else if (pl->nv == 4 && std::strcmp(e, "cells") == 0) pl->form = FORM_CELLS;
@@ -194,7 +194,7 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
             else if (pl->nv == 4 && std::strcmp(e, "pipe") == 0) pl->form = FORM_PIPE;
         }
         // channel-wise features patch the staged radii per channel pass, which needs the CTA-synchronous staging
-        if (pl->form == FORM_PIPE && chan_feat) pl->form = FORM_TILES;
+        if (pl->form == FORM_PIPE && chan_feat) pl->form = per_col >= 200.0 ? FORM_TILES : FORM_CELLS;
     }
     {   // layered entries of the tile kernel
         const int C = b->mode == MVX_MODE_FEATURES ? b->num_channels : 0;

@@ -1508,6 +1508,30 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// Shared-memory accesses of the hot loops by explicit 32-bit shared addresses: nvcc otherwise rebuilds the shared
+// window base (S2UR SR_CgaCtaId + ULEA) next to every access group inside the divergent loops.
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory");
+}
+
 template <int MODE, int CH, bool BINARY, bool O16>
 __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(const VoxParams P, const unsigned ntiles) {
     constexpr int LPR = 4, RX = kCellX, RY = kCellY, CZ = kCellZ;
@@ -1524,8 +1548,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
     uint64_t* const dfull = empty + ND;                                // slot s: the descriptor has landed
     int* const sOff = reinterpret_cast<int*>(dfull + ND);              // slot s: ring offset of the tile's entries
     int* const sNext = sOff + ND;                                      // slot s: next work item (cell x channel chunk) to hand out
-    float4* const wA_all = reinterpret_cast<float4*>(sNext + ND);
-    uint16_t* const wI_all = reinterpret_cast<uint16_t*>(wA_all + NW * kWarpList);
+    // warp lists: float4 words [WA0, WA0 + NW * kWarpList) of smem_q (record A of each listed atom), then their
+    // entry indices (u16).  Hot code indexes smem_q directly so that every access is a plain shared-memory one.
+    constexpr int WA0 = Q + kPipeSlots * ((int)sizeof(TileDesc) + 3 * 8 + 2 * 4) / 16;
+    uint32_t sq = smem_u32(smem_q);   // shared address of smem_q, pinned in a register
+    asm volatile("" : "+r"(sq));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int D = P.dim;
@@ -1534,9 +1561,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
     const int ES4 = P.es4;
     const uint32_t SC = (uint32_t)P.pipe_sc;   // largest tile (entries) this form takes
     const unsigned G = gridDim.x;
-
-    float4* const wA = wA_all + warp * kWarpList;
-    uint16_t* const wI = wI_all + warp * kWarpList;
 
     const float resf = (float)P.res;
     const float inv_res = 1.0f / resf;
@@ -1629,161 +1653,181 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
             const int z1 = min(D, z0 + P.tz);
             char* const out_mol = reinterpret_cast<char*>(P.out) + (size_t)mol * P.Cout * plane * es;
             const int ncells = kCellsXY * ((z1 - z0 + CZ - 1) / CZ);
-            const int nitems = ncells * ((P.c_end - P.c_begin + CH - 1) / CH);
             mbar_wait(&full[s], (it / ND) & 1u);
-            const int sb = sOff[s];   // this tile's entries: ring[sb + i * ES4 + {0, 1, 2, 3..}]
-            {
-                {
-                    // work items (cell x channel chunk) are handed out dynamically: the producer warp and warps that
-                    // drew heavy cells simply take fewer
-                    for (;;) {
-                        int item = 0;
-                        if (lane == 0) item = atomicAdd(&sNext[s], 1);
-                        item = __shfl_sync(0xffffffffu, item, 0);
-                        if (item >= nitems) break;
-                        const int chunk = item / ncells, cell = item - chunk * ncells;
-                        const int c0 = P.c_begin + chunk * CH;
-                        const int cz = cell / kCellsXY, cxy = cell % kCellsXY;
-                        const int cxl = cxy / NCY, cyl = cxy % NCY;
-                        const int lx = cxl * RX + rx, ly = cyl * RY + ry, lzv = cz * CZ + zq * 4;
-                        const int x = x0 + lx, y = y0 + ly, z = z0 + lzv;
-                        const bool valid = x < D && y < D && z < z1;
-                        const uint32_t lane_key = (uint32_t)lx | ((uint32_t)ly << 8);
-                        const float ox = (float)lx * resf, oy = (float)ly * resf;
-                        float oz[4];
+            const uint32_t sbq = sq + (uint32_t)sOff[s] * 16u;   // shared address of this tile's entries (ES4 float4 words each)
+            const uint32_t ebytes = (uint32_t)ES4 * 16u;
+            const uint32_t wAq = sq + (uint32_t)(WA0 + warp * kWarpList) * 16u;                       // warp list: record A
+            const uint32_t wIq = sq + (uint32_t)(WA0 + NW * kWarpList) * 16u + (uint32_t)(warp * kWarpList) * 2u;   // entry index
+            // cells are handed out dynamically: the producer warp and warps that drew heavy cells simply take fewer
+            for (;;) {
+                int cell = 0;
+                if (lane == 0) cell = atomicAdd(&sNext[s], 1);
+                cell = __shfl_sync(0xffffffffu, cell, 0);
+                if (cell >= ncells) break;
+                const int cz = cell / kCellsXY, cxy = cell % kCellsXY;
+                const int cxl = cxy / NCY, cyl = cxy % NCY;
+                const int lx = cxl * RX + rx, ly = cyl * RY + ry, lzv = cz * CZ + zq * 4;
+                const int x = x0 + lx, y = y0 + ly, z = z0 + lzv;
+                const bool valid = x < D && y < D && z < z1;
+                const uint32_t lane_key = (uint32_t)lx | ((uint32_t)ly << 8);
+                const float ox = (float)lx * resf, oy = (float)ly * resf;
+                float oz[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) oz[k] = (float)(z + k) * resf;   // grid-absolute, like the entries' z
+                for (int k = 0; k < 4; ++k) oz[k] = (float)(z + k) * resf;   // grid-absolute, like the entries' z
+                const int base0 = cz > 0 ? (int)sDesc[s].lend[cz - 1] : 0;
+                const int end = (int)sDesc[s].lend[cz];
+                int base = base0, wn = 0;
+                uint32_t mask_lo = 0u, mask_hi = 0u;
+                float acc[CH][4];
 
-                        float acc[CH][4];
+                // 1. warp filter over this cell's layer: atoms whose mask names the cell, order kept;
+                // 2. every lane tests the warp list against the nearest of its 4 voxels -> hit bitmasks
+                auto build_list = [&]() {
+                    wn = 0;
+                    while (base < end && wn <= kWarpList - 32) {
+                        const int i = base + lane;
+                        const bool in = (i < end) && ((lds32(sbq + (uint32_t)i * ebytes + 36u) >> cxy) & 1u);
+                        const uint32_t m = __ballot_sync(0xffffffffu, in);
+                        if (in) {
+                            const int pos = wn + __popc(m & ((1u << lane) - 1u));
+                            sts128(wAq + (uint32_t)pos * 16u, lds128(sbq + (uint32_t)i * ebytes));
+                            sts16(wIq + (uint32_t)pos * 2u, (uint32_t)i);
+                        }
+                        wn += __popc(m);
+                        base += 32;
+                    }
+                    __syncwarp();
+                    mask_lo = 0u; mask_hi = 0u;
+                    if (valid) {
+                        auto near_hit = [&](const float4 A) -> bool {
+                            const float dx = A.x - ox, dy = A.y - oy;
+                            const float tz_ = A.z - oz[0];
+                            const float dzc = fmaf(-resf, fminf(fmaxf(rintf(tz_ * inv_res), 0.f), 3.f), tz_);
+                            return fmaf(dzc, dzc, fmaf(dx, dx, dy * dy)) <= A.w;
+                        };
+                        const int n_lo = min(wn, 32);
+#pragma unroll 4
+                        for (int j = 0; j < n_lo; ++j)
+                            if (near_hit(lds128(wAq + (uint32_t)j * 16u))) mask_lo |= 1u << j;
+#pragma unroll 4
+                        for (int j = 32; j < wn; ++j)
+                            if (near_hit(lds128(wAq + (uint32_t)j * 16u))) mask_hi |= 1u << (j - 32);
+                    }
+                };
+                // 3. lane-private walk over the set bits, ascending (fixed fp32 summation order); the trip count
+                //    is the largest hit count of the warp
+                auto walk = [&](uint32_t mlo, uint32_t mhi, const int c0) {
+                    const int nmax = (int)__reduce_max_sync(0xffffffffu, (unsigned)(__popc(mlo) + __popc(mhi)));
+                    for (int h = 0; h < nmax; ++h) {
+                        if ((mlo | mhi) != 0u) {
+                            int j;
+                            if (mlo != 0u) { j = __ffs((int)mlo) - 1; mlo &= mlo - 1u; }
+                            else { j = 31 + __ffs((int)mhi); mhi &= mhi - 1u; }
+                            const uint32_t eb = sbq + lds16(wIq + (uint32_t)j * 2u) * ebytes;   // this atom's staged entry
+                            const float4 A = lds128(wAq + (uint32_t)j * 16u);
+                            const float4 Bv = lds128(eb + 16u);
+                            const float dx = A.x - ox, dy = A.y - oy;
+                            const float dxy = fmaf(dx, dx, dy * dy);
+                            // |s - r^2| <= tau (slightly widened) for any of the 4 voxels -> replay in fp64
+                            const float r2c = 0.5f * (A.w + Bv.x), tauh = 0.5f * (A.w - Bv.x) * 1.0001f + 1e-12f;
+                            float sk[4], w[4], dmin = 3.0e38f;
 #pragma unroll
-                        for (int c = 0; c < CH; ++c)
+                            for (int k = 0; k < 4; ++k) {
+                                const float dz = A.z - oz[k];
+                                sk[k] = fmaf(dz, dz, dxy);
+                                w[k] = (sk[k] < Bv.x) ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
+                                dmin = fminf(dmin, fabsf(sk[k] - r2c));
+                            }
+                            const uint32_t forb = __float_as_uint(Bv.z);
+                            if (dmin <= tauh || forb != kNoForb) {   // rare: tolerance band, or a block-cull plane in reach
+                                bool off[4];
+                                {   // block-cull emulation: voxels on the atom's forbidden planes take nothing from it
+                                    const uint32_t tx = forb ^ lane_key;
+                                    const bool row_off = (tx & 0xFFu) == 0u || (tx & 0xFF00u) == 0u;
+                                    const int dzf = (int)(forb >> 16) - z;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) acc[c][k] = 0.f;
-
-                        int base = cz > 0 ? (int)sDesc[s].lend[cz - 1] : 0;
-                        const int end = (int)sDesc[s].lend[cz];
-                        while (base < end) {
-                            // 1. warp filter over this cell's layer: atoms whose mask names the cell, order kept
-                            int wn = 0;
-                            while (base < end && wn <= kWarpList - 32) {
-                                const int i = base + lane;
-                                const bool in = (i < end) && ((__float_as_uint(ring[sb + i * ES4 + 2].y) >> cxy) & 1u);
-                                const uint32_t m = __ballot_sync(0xffffffffu, in);
-                                if (in) {
-                                    const int pos = wn + __popc(m & ((1u << lane) - 1u));
-                                    wA[pos] = ring[sb + i * ES4]; wI[pos] = (uint16_t)i;
+                                    for (int k = 0; k < 4; ++k) off[k] = row_off || dzf == k;
                                 }
-                                wn += __popc(m);
-                                base += 32;
-                            }
-                            __syncwarp();
-                            // 2. every lane tests the warp list against the nearest of its 4 voxels -> hit bitmasks
-                            uint32_t mask_lo = 0u, mask_hi = 0u;
-                            if (valid) {
-                                auto near_hit = [&](const float4 A) -> bool {
-                                    const float dx = A.x - ox, dy = A.y - oy;
-                                    const float tz_ = A.z - oz[0];
-                                    const float dzc = fmaf(-resf, fminf(fmaxf(rintf(tz_ * inv_res), 0.f), 3.f), tz_);
-                                    return fmaf(dzc, dzc, fmaf(dx, dx, dy * dy)) <= A.w;
-                                };
-                                const int n_lo = min(wn, 32);
-#pragma unroll 4
-                                for (int j = 0; j < n_lo; ++j)
-                                    if (near_hit(wA[j])) mask_lo |= 1u << j;
-#pragma unroll 4
-                                for (int j = 32; j < wn; ++j)
-                                    if (near_hit(wA[j])) mask_hi |= 1u << (j - 32);
-                            }
-                            // 3. lane-private walk over the set bits, ascending (fixed fp32 summation order)
-                            while (__any_sync(0xffffffffu, (mask_lo | mask_hi) != 0u)) {
-                                if ((mask_lo | mask_hi) != 0u) {
-                                    int j;
-                                    if (mask_lo != 0u) { j = __ffs((int)mask_lo) - 1; mask_lo &= mask_lo - 1u; }
-                                    else { j = 31 + __ffs((int)mask_hi); mask_hi &= mask_hi - 1u; }
-                                    const int eb = sb + (int)wI[j] * ES4;   // this atom's staged entry
-                                    const float4 A = wA[j];
-                                    const float4 Bv = ring[eb + 1];
-                                    const float dx = A.x - ox, dy = A.y - oy;
-                                    const float dxy = fmaf(dx, dx, dy * dy);
-                                    // |s - r^2| <= tau (slightly widened) for any of the 4 voxels -> replay in fp64
-                                    const float r2c = 0.5f * (A.w + Bv.x), tauh = 0.5f * (A.w - Bv.x) * 1.0001f + 1e-12f;
-                                    float sk[4], w[4], dmin = 3.0e38f;
+                                if (dmin <= tauh) {
+                                    const int n = (int)lds32(eb + 32u);
+                                    const float r32 = (MODE == 1) ? P.recs[n].r : Bv.w;
 #pragma unroll
                                     for (int k = 0; k < 4; ++k) {
-                                        const float dz = A.z - oz[k];
-                                        sk[k] = fmaf(dz, dz, dxy);
-                                        w[k] = (sk[k] < Bv.x) ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
-                                        dmin = fminf(dmin, fabsf(sk[k] - r2c));
-                                    }
-                                    const uint32_t forb = __float_as_uint(Bv.z);
-                                    if (dmin <= tauh || forb != kNoForb) {   // rare: tolerance band, or a block-cull plane in reach
-                                        bool off[4];
-                                        {   // block-cull emulation: voxels on the atom's forbidden planes take nothing from it
-                                            const uint32_t tx = forb ^ lane_key;
-                                            const bool row_off = (tx & 0xFFu) == 0u || (tx & 0xFF00u) == 0u;
-                                            const int dzf = (int)(forb >> 16) - z;
-#pragma unroll
-                                            for (int k = 0; k < 4; ++k) off[k] = row_off || dzf == k;
+                                        if (sk[k] >= Bv.x && !off[k]) {
+                                            const bool hit = sk[k] <= A.w && exact_hit(P.recs + n, r32, x, y, z + k, P.res, P.half_width);
+                                            w[k] = hit ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
                                         }
-                                        if (dmin <= tauh) {
-                                            const int n = (int)__float_as_uint(ring[eb + 2].x);
-                                            const float r32 = (MODE == 1) ? P.recs[n].r : Bv.w;
-#pragma unroll
-                                            for (int k = 0; k < 4; ++k) {
-                                                if (sk[k] >= Bv.x && !off[k]) {
-                                                    const bool hit = sk[k] <= A.w && exact_hit(P.recs + n, r32, x, y, z + k, P.res, P.half_width);
-                                                    w[k] = hit ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
-                                                }
-                                            }
-                                        }
-#pragma unroll
-                                        for (int k = 0; k < 4; ++k) w[k] = off[k] ? 0.f : w[k];
-                                    }
-                                    if (MODE == 0) {
-#pragma unroll
-                                        for (int k = 0; k < 4; ++k) acc[0][k] += w[k];
-                                    } else if (MODE == 1) {
-                                        const int ct = __float_as_int(Bv.w) - c0;
-#pragma unroll
-                                        for (int c = 0; c < CH; ++c)
-#pragma unroll
-                                            for (int k = 0; k < 4; ++k) acc[c][k] += (ct == c) ? w[k] : 0.f;
-                                    } else if (CH >= 4) {
-                                        const int fb = eb + 3 + (c0 >> 2);
-#pragma unroll
-                                        for (int c4 = 0; c4 < CH; c4 += 4) {
-                                            const float4 fv = ring[fb + (c4 >> 2)];
-                                            const float f[4] = {fv.x, fv.y, fv.z, fv.w};
-#pragma unroll
-                                            for (int k = 0; k < 4; ++k) {   // channel pairs through the packed FMA
-                                                ffma2(acc[c4][k], acc[c4 + 1][k], f[0], f[1], w[k]);
-                                                ffma2(acc[c4 + 2][k], acc[c4 + 3][k], f[2], f[3], w[k]);
-                                            }
-                                        }
-                                    } else {
-                                        const float f = reinterpret_cast<const float*>(ring + eb + 3)[c0];
-#pragma unroll
-                                        for (int k = 0; k < 4; ++k) acc[0][k] = fmaf(f, w[k], acc[0][k]);
                                     }
                                 }
-                            }
-                            __syncwarp();
-                        }
-                        if (valid) {
-                            char* p = out_mol + ((size_t)c0 * plane + ((size_t)x * D + y) * D + z) * es;
-                            const size_t pstride = plane * es;
-                            if (c0 + CH <= P.c_end) {
 #pragma unroll
-                                for (int c = 0; c < CH; ++c, p += pstride) store_vox<O16>(p, acc[c], P.out_kind);
+                                for (int k = 0; k < 4; ++k) w[k] = off[k] ? 0.f : w[k];
+                            }
+                            if (MODE == 0) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) acc[0][k] += w[k];
+                            } else if (MODE == 1) {
+                                const int ct = __float_as_int(Bv.w) - c0;
+#pragma unroll
+                                for (int c = 0; c < CH; ++c)
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) acc[c][k] += (ct == c) ? w[k] : 0.f;
+                            } else if (CH >= 4) {
+                                const uint32_t fb = eb + 48u + (uint32_t)c0 * 4u;
+#pragma unroll
+                                for (int c4 = 0; c4 < CH; c4 += 4) {
+                                    const float4 fv = lds128(fb + (uint32_t)c4 * 4u);
+                                    const float f[4] = {fv.x, fv.y, fv.z, fv.w};
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {   // channel pairs through the packed FMA
+                                        ffma2(acc[c4][k], acc[c4 + 1][k], f[0], f[1], w[k]);
+                                        ffma2(acc[c4 + 2][k], acc[c4 + 3][k], f[2], f[3], w[k]);
+                                    }
+                                }
                             } else {
+                                const float f = __uint_as_float(lds32(eb + 48u + (uint32_t)c0 * 4u));
 #pragma unroll
-                                for (int c = 0; c < CH; ++c, p += pstride)
-                                    if (c0 + c < P.c_end) store_vox<O16>(p, acc[c], P.out_kind);
+                                for (int k = 0; k < 4; ++k) acc[0][k] = fmaf(f, w[k], acc[0][k]);
                             }
                         }
-                        if (tid == 0) produce(false);   // keep the ring topped up without ever blocking
                     }
+                    __syncwarp();
+                };
+                auto clear = [&]() {
+#pragma unroll
+                    for (int c = 0; c < CH; ++c)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc[c][k] = 0.f;
+                };
+                auto store = [&](const int c0) {
+                    if (valid) {
+                        char* p = out_mol + ((size_t)c0 * plane + ((size_t)x * D + y) * D + z) * es;
+                        const size_t pstride = plane * es;
+                        if (c0 + CH <= P.c_end) {
+#pragma unroll
+                            for (int c = 0; c < CH; ++c, p += pstride) store_vox<O16>(p, acc[c], P.out_kind);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < CH; ++c, p += pstride)
+                                if (c0 + c < P.c_end) store_vox<O16>(p, acc[c], P.out_kind);
+                        }
+                    }
+                };
+
+                // When the whole layer fits one warp list (the common case) its hit masks serve every channel chunk;
+                // otherwise each chunk walks the layer's list rounds again.
+                build_list();
+                const bool single = base >= end;
+                for (int c0 = P.c_begin; c0 < P.c_end; c0 += CH) {
+                    clear();
+                    if (!single && c0 != P.c_begin) { base = base0; build_list(); }
+                    for (;;) {
+                        walk(mask_lo, mask_hi, c0);
+                        if (base >= end) break;
+                        build_list();
+                    }
+                    store(c0);
                 }
+                if (tid == 0) produce(false);   // keep the ring topped up without ever blocking
             }
         } else if (total == 0u) {
             unsigned t = tile;
