@@ -48,12 +48,12 @@ struct Plan {
     int ncol, nzc, tz, maxcols, nv;
     float tau_lin, tau_quad;
     // workspace offsets (bytes)
-    size_t off_status, off_recs, off_colrange, off_bins, off_lists, off_entries, total;
+    size_t off_status, off_recs, off_colrange, off_alayers, off_bins, off_lists, off_entries, total;
     int masks;   // expand pass precomputes the cell masks (<= 64 cells per column)
     int form;        // voxelize kernel form, see enum Form
     int ncell;
     int nlayers, zl, es4;
-    size_t off_lent, off_lmask, off_lbins, off_tdesc;
+    size_t off_lent, off_lmask, off_lbins, off_tdesc, off_kcnt, off_lids;   // kcnt: key counts, then key cursors
     int pipe_sc;   // pipelined form: largest tile (entries) it takes
 };
 
@@ -176,7 +176,6 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     pl->off_recs = off;     off += align_up(N * sizeof(mvx::AtomRec));
     pl->off_colrange = off; off += align_up(N * sizeof(uint32_t));
     pl->off_bins = off;     off += align_up(B * (size_t)pl->ncol * sizeof(uint2));
-    pl->off_lists = off;    off += align_up(N * (size_t)pl->maxcols * sizeof(uint32_t));
     const int layers = pl->nzc * ((tz + mvx::kCellZ - 1) / mvx::kCellZ);
     pl->ncell = layers * mvx::kCellsXY;
     pl->masks = pl->nv == 4 && pl->ncell <= 64;
@@ -209,8 +208,13 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
         pl->off_lmask = off; off += align_up(nle * sizeof(uint32_t));
         pl->off_lbins = off; off += align_up(layered(pl->form) ? B * (size_t)pl->ncol * (size_t)layers * sizeof(uint2) : 0);
         pl->off_tdesc = off; off += align_up(pl->form == FORM_PIPE ? B * (size_t)pl->ncol * (size_t)pl->nzc * sizeof(mvx::TileDesc) : 0);
+        const size_t nkeys = layered(pl->form) ? B * (size_t)pl->ncol * (size_t)layers : 0;
+        pl->off_kcnt = off;  off += align_up(2 * nkeys * sizeof(uint32_t));
+        pl->off_lids = off;  off += align_up(nle * sizeof(uint32_t));
         pl->pipe_sc = mvx::kPipeRingQ / 2 / pl->es4;   // the pipelined form takes tiles up to half its ring
     }
+    pl->off_alayers = off;  off += align_up(layered(pl->form) ? N * sizeof(uint32_t) : 0);
+    pl->off_lists = off;    off += align_up(layered(pl->form) ? 0 : N * (size_t)pl->maxcols * sizeof(uint32_t));
     pl->off_entries = off;  off += align_up(pl->form == FORM_CELLS ? N * (size_t)pl->maxcols * sizeof(mvx::ColEntry) : 0);
     pl->total = off;
     return MVX_OK;
@@ -343,8 +347,8 @@ int mvx_launches_per_call(const mvx_grid_spec* spec, const mvx_batch* batch) {
     if (batch->num_mols == 0) return 0;
     const bool chan_feat = batch->mode == MVX_MODE_FEATURES && spec->radii_type == MVX_RADII_CHANNEL_WISE;
     int nvox = chan_feat ? batch->num_channels : 1;
-    const int nbin = bin_groups(batch->num_mols, pl.ncol) <= 1 ? 1 : 2;
-    const int nexp = (pl.form != FORM_ROWS && (batch->total_atoms > 0 || pl.form == FORM_PIPE)) ? 1 : 0;
+    const int nbin = layered(pl.form) ? (batch->total_atoms > 0 ? 3 : 1) : (bin_groups(batch->num_mols, pl.ncol) <= 1 ? 1 : 2);   // scan, place, build
+    const int nexp = (pl.form == FORM_CELLS && batch->total_atoms > 0) ? 1 : 0;
     return (batch->total_atoms > 0 ? 1 : 0) + nbin + nexp + nvox * (pl.form == FORM_PIPE ? 2 : 1);   // prep + bin + expand + voxelize
 }
 
@@ -372,6 +376,8 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
     const int64_t N = batch->total_atoms;
     const int C = batch->mode == MVX_MODE_SINGLE ? 1 : batch->num_channels;
     MVX_CUDA_OK(cudaMemsetAsync(status, 0, kAlign, st));
+    if (layered(pl.form))   // key counts + key cursors of the layered binning
+        MVX_CUDA_OK(cudaMemsetAsync(ws + pl.off_kcnt, 0, 2 * (size_t)batch->num_mols * pl.ncol * pl.nlayers * sizeof(uint32_t), st));
     prof_mark(st, 0);
 
     if (N > 0) {
@@ -383,12 +389,40 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         pp.centers = batch->centers; pp.centers_f64 = batch->centers_dtype == MVX_F64;
         pp.types = batch->types; pp.radii = batch->radii; pp.transforms = batch->transforms;
         pp.recs = recs; pp.colrange = colrange; pp.status = status;
+        pp.alayers = layered(pl.form) ? (uint32_t*)(ws + pl.off_alayers) : nullptr;
+        pp.kcnt = layered(pl.form) ? (uint32_t*)(ws + pl.off_kcnt) : nullptr;
+        pp.nzc = pl.nzc; pp.tz = pl.tz; pp.ncol = pl.ncol; pp.nl = pl.nlayers; pp.tau_lin = pl.tau_lin; pp.tau_quad = pl.tau_quad;
         const unsigned grid = (unsigned)((N + 255) / 256);
         mvx::mvx_prep_kernel<<<grid, 256, 0, st>>>(pp);
         MVX_CUDA_OK(cudaGetLastError());
     }
     prof_mark(st, 1);
-    {
+    if (layered(pl.form)) {   // per-layer entries (+ tile descriptors) straight from the per-atom column / layer words
+        mvx::LBinParams lp;
+        lp.res = pl.geo.res; lp.half_width = pl.geo.half_width; lp.sigma = spec->sigma;
+        lp.tau_lin = pl.tau_lin; lp.tau_quad = pl.tau_quad;
+        lp.B = B; lp.ncol = pl.ncol; lp.ncx = pl.geo.ncx; lp.maxcols = pl.maxcols; lp.zl = pl.zl; lp.nl = pl.nlayers;
+        lp.nzc = pl.nzc; lp.tz = pl.tz; lp.dim = spec->dimension; lp.mode = batch->mode;
+        lp.C = batch->mode == MVX_MODE_FEATURES ? C : 0; lp.es4 = pl.es4;
+        lp.mol_offsets = batch->mol_offsets; lp.colrange = colrange; lp.alayers = (const uint32_t*)(ws + pl.off_alayers);
+        lp.recs = recs; lp.types = batch->types; lp.features = batch->features;
+        lp.bins = bins; lp.lbins = (uint2*)(ws + pl.off_lbins);
+        lp.tdesc = pl.form == FORM_PIPE ? (mvx::TileDesc*)(ws + pl.off_tdesc) : nullptr;
+        lp.lent = (float4*)(ws + pl.off_lent); lp.lmask = (uint32_t*)(ws + pl.off_lmask);
+        const size_t nkeys = (size_t)B * pl.ncol * pl.nlayers;
+        lp.N = N; lp.kcnt = (const uint32_t*)(ws + pl.off_kcnt); lp.cursor = (uint32_t*)(ws + pl.off_kcnt) + nkeys;
+        lp.lids = (uint32_t*)(ws + pl.off_lids);
+        if ((nkeys + 7) / 8 > 0x7fffffffULL) return fail(MVX_ERR_BAD_SHAPE, "batch too large for one launch; split it");
+        const size_t smem = 2 * (size_t)pl.ncol * sizeof(uint32_t);
+        mvx::mvx_lscan_kernel<<<(unsigned)B, 256, smem, st>>>(lp);
+        MVX_CUDA_OK(cudaGetLastError());
+        if (N > 0) {
+            mvx::mvx_lplace_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(lp);
+            MVX_CUDA_OK(cudaGetLastError());
+            mvx::mvx_lbuild_kernel<<<(unsigned)((nkeys + 7) / 8), 256, 0, st>>>(lp);
+            MVX_CUDA_OK(cudaGetLastError());
+        }
+    } else {
         mvx::BinParams bp;
         bp.B = B; bp.ncol = pl.ncol; bp.ncx = pl.geo.ncx; bp.maxcols = pl.maxcols;
         bp.mol_offsets = batch->mol_offsets; bp.colrange = colrange; bp.bins = bins; bp.lists = lists;
@@ -402,7 +436,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
             mvx::mvx_bin_fill_kernel<<<(unsigned)(B * groups), 256, smem, st>>>(bp, groups);
         }
         MVX_CUDA_OK(cudaGetLastError());
-        if (pl.form != FORM_ROWS && (N > 0 || pl.form == FORM_PIPE)) {   // column lists -> staged-ready entries (+ tile descriptors)
+        if (pl.form == FORM_CELLS && N > 0) {   // column lists -> staged-ready entries
             mvx::ExpandParams ep;
             ep.res = pl.geo.res; ep.half_width = pl.geo.half_width; ep.sigma = spec->sigma;
             ep.tau_lin = pl.tau_lin; ep.tau_quad = pl.tau_quad;
@@ -410,14 +444,8 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
             ep.maxcols = pl.maxcols; ep.mode = batch->mode; ep.masks = legacy_masks; ep.B = B;
             ep.mol_offsets = batch->mol_offsets; ep.recs = recs; ep.bins = bins; ep.lists = lists;
             ep.types = batch->types; ep.entries = entries;
-            ep.nlayers = pl.nlayers; ep.zl = pl.zl; ep.es4 = pl.es4;
-            ep.C = batch->mode == MVX_MODE_FEATURES ? C : 0; ep.features = batch->features;
-            ep.lent = (float4*)(ws + pl.off_lent); ep.lmask = (uint32_t*)(ws + pl.off_lmask);
-            ep.lbins = (uint2*)(ws + pl.off_lbins);
-            ep.tdesc = pl.form == FORM_PIPE ? (mvx::TileDesc*)(ws + pl.off_tdesc) : nullptr;
             const long long warps = (long long)B * pl.ncol;
-            if (layered(pl.form)) mvx::mvx_expand_layers_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(ep);
-            else mvx::mvx_expand_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(ep);
+            mvx::mvx_expand_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(ep);
             MVX_CUDA_OK(cudaGetLastError());
         }
     }

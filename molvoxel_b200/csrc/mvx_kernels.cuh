@@ -22,6 +22,9 @@ constexpr int kTile = 8;          // column footprint in x and y (voxels)
 constexpr int kThreads = 256;     // voxelize CTA size
 constexpr int kMaxCand = 128;     // candidates staged per round
 constexpr float kLog2e = 1.4426950408889634f;
+// cell shape of the warp-cell kernels: 2 x 4 x 16 voxels (4 lanes of one float4 along z per row)
+constexpr int kCellX = 2, kCellY = 4, kCellZ = 16;
+constexpr int kCellsXY = (kTile / kCellX) * (kTile / kCellY);   // 8 cells per z layer of a tile
 
 enum : int { kFlagBadType = 1, kFlagRadiusOverMax = 2 };
 
@@ -60,6 +63,12 @@ struct PrepParams {
     AtomRec* recs;
     uint32_t* colrange;
     int* status;
+    // layered forms: per atom, the 16-voxel z layers (global layer index = z chunk * layers-per-chunk + layer) its
+    // cutoff sphere reaches; nullptr otherwise
+    uint32_t* alayers;
+    uint32_t* kcnt;     // layered forms: atoms per (molecule, column, layer), counted here with fire-and-forget atomics
+    int nzc, tz, ncol, nl;
+    float tau_lin, tau_quad;
 };
 
 struct BinParams {
@@ -92,9 +101,6 @@ struct __align__(16) TileDesc {
 };
 static_assert(sizeof(TileDesc) == 32, "TileDesc layout");
 
-// cell shape of the warp-cell kernel: 2 x 4 x 16 voxels (4 lanes of one float4 along z per row)
-constexpr int kCellX = 2, kCellY = 4, kCellZ = 16;
-constexpr int kCellsXY = (kTile / kCellX) * (kTile / kCellY);   // 8 cells per z layer of a tile
 
 struct ExpandParams {
     double res, half_width, sigma;
@@ -106,16 +112,6 @@ struct ExpandParams {
     const uint32_t* lists;
     const int32_t* types;
     ColEntry* entries;   // CELLS form: one 48-byte record per (column, atom)
-    // TILES form: entries regrouped per 16-voxel z layer, feature rows appended
-    int nlayers;        // nzc * ceil(tz / 16)  (<= 32)
-    int zl;             // capacity: layers one entry can reach
-    int es4;            // float4 words per layered entry: 3 + ceil(C / 4) (features) or 3
-    int C;              // feature row length (FEATURES) or 0
-    const float* features;
-    float4* lent;       // column with ids [e0, e0 + cnt) owns lent[e0 * zl * es4, (e0 + cnt) * zl * es4)
-    uint32_t* lmask;    // per layered entry: 8-bit mask of the layer's cells its cutoff sphere reaches
-    uint2* lbins;       // (start relative to the column's layered segment, count) per (molecule, column, layer)
-    TileDesc* tdesc;    // per (molecule, column, z chunk), or nullptr
 };
 
 struct VoxParams {
@@ -252,6 +248,36 @@ __global__ void __launch_bounds__(256) mvx_prep_kernel(const PrepParams P) {
     rec.pad = 0;
     P.recs[n] = rec;
     P.colrange[n] = cr;
+    if (P.alayers != nullptr) {
+        uint32_t m = 0u;
+        if (keep) {
+            const float resf = (float)g.res;
+            const float r2 = r32 * r32;
+            const float r2hi = r2 + (r32 * P.tau_lin + r2 * P.tau_quad);
+            const float lim = r2hi + 1e-4f * (1.f + r2hi);
+            const float az = (float)(p[2] + g.half_width);
+            const int ncz_max = (P.tz + kCellZ - 1) / kCellZ;
+            for (int zc = 0; zc < P.nzc; ++zc) {
+                const int z0 = zc * P.tz, z1 = min(g.dim, z0 + P.tz);
+                for (int cz = 0; cz < ncz_max; ++cz) {
+                    const int lo = z0 + cz * kCellZ, hi = min(lo + kCellZ, z1);
+                    if (lo >= hi || v1[2] < lo || v0[2] >= hi) continue;
+                    const float bhz = 0.5f * (hi - lo - 1) * resf;
+                    const float ez = fmaxf(fabsf(az - (lo * resf + bhz)) - bhz, 0.f);
+                    if (ez * ez <= lim) m |= 1u << (zc * ncz_max + cz);
+                }
+            }
+        }
+        P.alayers[n] = m;
+        if (m != 0u) {   // keep is true: count this atom under every (column, layer) key it belongs to
+            const int cx0 = cr & 0xFF, cx1 = (cr >> 8) & 0xFF, cy0 = (cr >> 16) & 0xFF, cy1 = (cr >> 24) & 0xFF;
+            for (int cx = cx0; cx <= cx1; ++cx)
+                for (int cy = cy0; cy <= cy1; ++cy) {
+                    uint32_t* k = P.kcnt + ((size_t)mol * P.ncol + (size_t)(cx * g.ncx + cy)) * P.nl;
+                    for (uint32_t b = m; b != 0u; b &= b - 1u) atomicAdd(k + (__ffs((int)b) - 1), 1u);
+                }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -435,175 +461,213 @@ __global__ void __launch_bounds__(256) mvx_expand_kernel(const ExpandParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// expand (layered form, feeds the tile kernel): one warp per (molecule, column).  The column's atoms are
-// regrouped per 16-voxel z layer (an atom reaching two layers is written twice), each as a record that is
-// ready to use from shared memory: tile-relative fp32 position, cutoff band, Gaussian coefficient, packed
-// forbidden planes, type / radius, atom id, followed by its feature row; beside it an 8-bit mask of the
-// layer's 2 x 4 x 16-voxel cells its cutoff sphere reaches.  Order inside a layer = ascending atom id.
-// The voxelize kernel then stages a whole tile with ONE flat coalesced copy and no per-atom arithmetic.
+// layered binning (feeds the tile and pipelined kernels): the atoms of a column are grouped per 16-voxel z
+// layer (an atom reaching two layers is written twice), each as a record that is ready to use from shared
+// memory — tile-relative fp32 position, cutoff band, Gaussian coefficient, packed forbidden planes, type /
+// radius, atom id, the 8-bit mask of the layer's 2 x 4 x 16-voxel cells its cutoff sphere reaches — followed
+// by its feature row.  Order inside a layer = ascending atom id (the reference's summation order).
+//
+// A counting sort keyed by (molecule, column, layer), with work proportional to the (atom, key) pairs:
+//   prep   counts the pairs per key (atomics without return value);
+//   scan   one CTA per molecule: prefix sums over layers and columns -> segment offsets, tile descriptors;
+//   place  one thread per atom: claims a slot in each of its keys' segments (any order) and drops its id there;
+//   build  one warp per key: ranks the segment's ids (rank = number of smaller ids, so the final order is the
+//          ascending atom order whatever order the slots were claimed in) and writes the entries, one lane per entry.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) mvx_expand_layers_kernel(const ExpandParams P) {
-    __shared__ uint32_t s_lm[8 * kExpandSmemMasks];   // layer masks of the first 512 atoms of each warp's column
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-    if (gw >= (long long)P.B * P.ncol) return;
-    const int mol = (int)(gw / P.ncol), col = (int)(gw % P.ncol);
-    const uint2 bin = P.bins[gw];
-    if (bin.y == 0) {
-        if (P.tdesc != nullptr && lane < P.nzc) {
-            TileDesc d;
-            d.start = 0ull; d.total = 0u; d.lend[0] = d.lend[1] = d.lend[2] = d.lend[3] = 0u; d.pad = 0u;
-            P.tdesc[(size_t)gw * P.nzc + lane] = d;
-        }
-        return;
+struct LBinParams {
+    double res, half_width, sigma;
+    float tau_lin, tau_quad;
+    int B, ncol, ncx, maxcols, zl, nl, nzc, tz, dim, mode, C, es4;
+    int64_t N;
+    const int32_t* mol_offsets;
+    const uint32_t* colrange;
+    const uint32_t* alayers;
+    const AtomRec* recs;
+    const int32_t* types;
+    const float* features;
+    const uint32_t* kcnt;   // per key: pairs counted by prep
+    uint32_t* cursor;       // per key: slots claimed so far (zeroed per call)
+    uint32_t* lids;         // per layered slot: atom id (unordered inside a segment)
+    uint2* bins;        // per (molecule, column): (offset in the molecule's layered segment, layered entries)
+    uint2* lbins;       // per (molecule, column, layer): (offset in the column's segment, count)
+    TileDesc* tdesc;    // per (molecule, column, z chunk), or nullptr
+    float4* lent;       // molecule m owns entries [mol_offsets[m] * maxcols * zl, ...), es4 float4 words each
+    uint32_t* lmask;    // per layered entry: its 8-bit cell mask (tile form)
+};
+
+__global__ void __launch_bounds__(256) mvx_lscan_kernel(const LBinParams P) {
+    extern __shared__ uint32_t s_u32[];
+    uint32_t* s_cnt = s_u32;            // [ncol] layered totals of the molecule's columns
+    uint32_t* s_off = s_u32 + P.ncol;   // [ncol] their exclusive prefix sums
+    const int mol = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int nl = P.nl;
+    const int ncz_max = (P.tz + kCellZ - 1) / kCellZ;
+    const size_t lseg = (size_t)P.mol_offsets[mol] * (size_t)P.maxcols * (size_t)P.zl;
+    for (int col = warp; col < P.ncol; col += nwarps) {
+        const size_t gcol = (size_t)mol * P.ncol + col;
+        const uint32_t c = lane < nl ? P.kcnt[gcol * nl + lane] : 0u;
+        const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) s_cnt[col] = tot;
     }
-    const size_t base = (size_t)P.mol_offsets[mol] * (size_t)P.maxcols + bin.x;
-    const size_t lbase = base * (size_t)P.zl;
-    float4* lent = P.lent + lbase * (size_t)P.es4;
-    uint32_t* lmask = P.lmask + lbase;
+    __syncthreads();
+    if (warp == 0) bin_scan_counts(s_cnt, s_off, P.ncol, lane);
+    __syncthreads();
+    for (int col = warp; col < P.ncol; col += nwarps) {
+        const size_t gcol = (size_t)mol * P.ncol + col;
+        const uint32_t my_cnt = lane < nl ? P.kcnt[gcol * nl + lane] : 0u;
+        uint32_t xs = my_cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, xs, d); if (lane >= d) xs += y; }
+        const uint32_t my_off = xs - my_cnt;   // lane L: first slot of layer L in the column's segment
+        if (lane < nl) P.lbins[gcol * nl + lane] = make_uint2(my_off, my_cnt);
+        if (lane == 0) P.bins[gcol] = make_uint2(s_off[col], s_cnt[col]);
+        if (P.tdesc != nullptr) {   // tile descriptors of this column's z chunks (the layers of a chunk are consecutive)
+            for (int zc = 0; zc < P.nzc; ++zc) {
+                const int L0 = zc * ncz_max;
+                const int ncz = (min(P.dim, (zc + 1) * P.tz) - zc * P.tz + kCellZ - 1) / kCellZ;
+                const uint32_t o0 = __shfl_sync(0xffffffffu, my_off, L0);
+                uint32_t e[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    e[k] = __shfl_sync(0xffffffffu, my_off + my_cnt, min(L0 + min(k, ncz - 1), 31)) - o0;
+                if (lane == 0) {
+                    TileDesc d;
+                    d.start = (unsigned long long)lseg + s_off[col] + o0; d.total = e[3];
+                    d.lend[0] = e[0]; d.lend[1] = e[1]; d.lend[2] = e[2]; d.lend[3] = e[3]; d.pad = 0u;
+                    P.tdesc[gcol * P.nzc + zc] = d;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) mvx_lplace_kernel(const LBinParams P) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= P.N) return;
+    const uint32_t m = P.alayers[n];
+    if (m == 0u) return;
+    int lo = 0, hi = P.B;   // offs[lo] <= n < offs[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)P.mol_offsets[mid] <= n) lo = mid; else hi = mid;
+    }
+    const int mol = lo;
+    const size_t lseg = (size_t)P.mol_offsets[mol] * (size_t)P.maxcols * (size_t)P.zl;
+    const uint32_t cr = P.colrange[n];
+    const int cx0 = cr & 0xFF, cx1 = (cr >> 8) & 0xFF, cy0 = (cr >> 16) & 0xFF, cy1 = (cr >> 24) & 0xFF;
+    for (int cx = cx0; cx <= cx1; ++cx)
+        for (int cy = cy0; cy <= cy1; ++cy) {
+            const size_t gcol = (size_t)mol * P.ncol + (size_t)(cx * P.ncx + cy);
+            const uint32_t coff = P.bins[gcol].x;
+            for (uint32_t b = m; b != 0u; b &= b - 1u) {
+                const size_t key = gcol * P.nl + (__ffs((int)b) - 1);
+                const uint32_t pos = atomicAdd(P.cursor + key, 1u);
+                P.lids[lseg + coff + P.lbins[key].x + pos] = (uint32_t)n;
+            }
+        }
+}
+
+constexpr int kLBuildIds = 256;   // ids of a segment ranked from shared memory per round
+
+__global__ void __launch_bounds__(256) mvx_lbuild_kernel(const LBinParams P) {
+    __shared__ __align__(16) uint32_t s_ids[8][kLBuildIds];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long key = (long long)blockIdx.x * 8 + warp;
+    if (key >= (long long)P.B * P.ncol * P.nl) return;
+    const uint2 lb = P.lbins[key];
+    const int S = (int)lb.y;
+    if (S == 0) return;
+    const int L = (int)(key % P.nl);
+    const long long gcol = key / P.nl;
+    const int col = (int)(gcol % P.ncol), mol = (int)(gcol / P.ncol);
+    const size_t seg = (size_t)P.mol_offsets[mol] * (size_t)P.maxcols * (size_t)P.zl + P.bins[gcol].x + lb.x;
+    const uint32_t* ids = P.lids + seg;
+    uint32_t* buf = s_ids[warp];
+
     const int x0 = (col / P.ncx) * kTile, y0 = (col % P.ncx) * kTile;
     const double ox0 = (double)x0 * P.res - P.half_width, oy0 = (double)y0 * P.res - P.half_width;
     const float resf = (float)P.res;
     const float bhx = 0.5f * (kCellX - 1) * resf, bhy = 0.5f * (kCellY - 1) * resf;
     const int ncz_max = (P.tz + kCellZ - 1) / kCellZ;
-    const int nl = P.nlayers;
+    const int zc = L / ncz_max, cz = L - zc * ncz_max;
+    const int z0 = zc * P.tz, z1 = min(P.dim, z0 + P.tz);
+    const int zlo = z0 + cz * kCellZ, zhi = min(zlo + kCellZ, z1);
+    const float bhz = 0.5f * (zhi - zlo - 1) * resf;
+    const float zmid = zlo * resf + bhz;
 
-    auto layer_z = [&](int L, int& lo, int& hi) {   // voxel z range [lo, hi) of global layer L (empty if lo >= hi)
-        const int zc = L / ncz_max, cz = L - zc * ncz_max;
-        const int z0 = zc * P.tz, z1 = min(P.dim, z0 + P.tz);
-        lo = z0 + cz * kCellZ;
-        hi = min(lo + kCellZ, z1);
-    };
-    auto layer_ez2 = [&](float az, int lo, int hi) -> float {   // squared z distance to the layer's voxel-centre slab
-        const float bhz = 0.5f * (hi - lo - 1) * resf;
-        const float ez = fmaxf(fabsf(az - (lo * resf + bhz)) - bhz, 0.f);
-        return ez * ez;
-    };
-    auto band_of = [&](float r, float& r2hi, float& r2lo) {
+    for (int i0 = 0; i0 < S; i0 += 32) {   // 32 entries per round, one per lane
+        const int i = i0 + lane;
+        const uint32_t n = i < S ? ids[i] : 0xFFFFFFFFu;
+        // rank = ids of the segment smaller than mine (ids are distinct): the entry's place in ascending atom order
+        uint32_t rank = 0;
+        for (int j0 = 0; j0 < S; j0 += kLBuildIds) {
+            const int nj = min(kLBuildIds, S - j0);
+            if (S > kLBuildIds || i0 == 0) {   // a segment that fits is staged once
+                __syncwarp();
+                for (int j = lane; j < nj; j += 32) buf[j] = ids[j0 + j];
+                __syncwarp();
+            }
+            int j = 0;
+            for (; j + 4 <= nj; j += 4) {
+                const uint4 v = *reinterpret_cast<const uint4*>(buf + j);
+                rank += (v.x < n) + (v.y < n) + (v.z < n) + (v.w < n);
+            }
+            for (; j < nj; ++j) rank += buf[j] < n;
+        }
+        if (i >= S) continue;
+        const size_t slot = seg + rank;
+        const AtomRec rec = P.recs[n];
+        const float r = rec.r;
         const float r2 = r * r;
         const float tau = r * P.tau_lin + r2 * P.tau_quad;
-        r2hi = r2 + tau; r2lo = r2 - tau;
-    };
-    auto layer_mask_of = [&](uint32_t i) -> uint32_t {
-        const AtomRec rec = P.recs[P.lists[base + i]];
-        float r2hi, r2lo;
-        band_of(rec.r, r2hi, r2lo);
+        const float r2hi = r2 + tau, r2lo = r2 - tau;
+        const double rs = (double)r * P.sigma;
+        const float kc = (float)(-0.5 * 1.4426950408889634 / (rs * rs));
+        const float ax = (float)(rec.px - ox0), ay = (float)(rec.py - oy0), az = (float)(rec.pz + P.half_width);
+        // forbidden planes (block-cull emulation) are kept only where the cutoff sphere can reach them, so
+        // that most entries carry "none" and the voxelize kernels skip the cull arithmetic
+        const int fx = rec.fx - x0, fy = rec.fy - y0;
+        const float rr = r * 1.001f + 0.01f * resf;
+        const bool kx = rec.fx >= 0 && fx >= 0 && fx < kTile && fabsf(ax - fx * resf) <= rr;
+        const bool ky = rec.fy >= 0 && fy >= 0 && fy < kTile && fabsf(ay - fy * resf) <= rr;
+        const bool kz = rec.fz >= 0 && fabsf(az - rec.fz * resf) <= rr;
+        const uint32_t forb = (uint32_t)(kx ? fx : 0xFF) | ((uint32_t)(ky ? fy : 0xFF) << 8) |
+                              ((uint32_t)(kz ? rec.fz : 0xFFFF) << 16);
+        // cells of this layer reached by the cutoff sphere: exact sphere / voxel-centre-box test
+        const float ez = fmaxf(fabsf(az - zmid) - bhz, 0.f);
+        const float ez2 = ez * ez;
         const float lim = r2hi + 1e-4f * (1.f + r2hi);
-        const float az = (float)(rec.pz + P.half_width);
-        uint32_t m = 0u;
-        for (int L = 0; L < nl; ++L) {
-            int lo, hi;
-            layer_z(L, lo, hi);
-            if (lo >= hi || rec.zhi < lo || rec.zlo >= hi) continue;
-            if (layer_ez2(az, lo, hi) <= lim) m |= 1u << L;
-        }
-        return m;
-    };
-
-    uint32_t* wl = s_lm + warp * kExpandSmemMasks;
-    for (uint32_t i = lane; i < bin.y; i += 32) {
-        const uint32_t m = layer_mask_of(i);
-        if (i < (uint32_t)kExpandSmemMasks) wl[i] = m;
-    }
-    __syncwarp();
-    auto lm = [&](uint32_t i) -> uint32_t { return i < (uint32_t)kExpandSmemMasks ? wl[i] : layer_mask_of(i); };
-
-    uint32_t my_cnt = 0;   // lane L: atoms reaching layer L
-    for (int L = 0; L < nl; ++L) {
-        uint32_t cnt = 0;
-        for (uint32_t i0 = 0; i0 < bin.y; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            cnt += __popc(__ballot_sync(0xffffffffu, i < bin.y && ((lm(i) >> L) & 1u)));
-        }
-        if (lane == L) my_cnt = cnt;
-    }
-    uint32_t x = my_cnt;
+        uint32_t cm = 0u;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
-    const uint32_t my_off = x - my_cnt;
-    if (lane < nl) P.lbins[(size_t)gw * nl + lane] = make_uint2(my_off, my_cnt);
-    if (P.tdesc != nullptr) {   // tile descriptors of this column's z chunks (layers of a chunk are consecutive)
-        for (int zc = 0; zc < P.nzc; ++zc) {
-            const int L0 = zc * ncz_max;
-            const int ncz = (min(P.dim, (zc + 1) * P.tz) - zc * P.tz + kCellZ - 1) / kCellZ;
-            const uint32_t o0 = __shfl_sync(0xffffffffu, my_off, L0);
-            uint32_t e[4];
+        for (int ix = 0; ix < kTile / kCellX; ++ix) {
+            const float ex = fmaxf(fabsf(ax - ((ix * kCellX) * resf + bhx)) - bhx, 0.f);
+            const float exz = fmaf(ex, ex, ez2);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                e[k] = __shfl_sync(0xffffffffu, my_off + my_cnt, min(L0 + min(k, ncz - 1), 31)) - o0;
-            if (lane == 0) {
-                TileDesc d;
-                d.start = (unsigned long long)lbase + o0; d.total = e[3];
-                d.lend[0] = e[0]; d.lend[1] = e[1]; d.lend[2] = e[2]; d.lend[3] = e[3]; d.pad = 0u;
-                P.tdesc[(size_t)gw * P.nzc + zc] = d;
+            for (int iy = 0; iy < kTile / kCellY; ++iy) {
+                const float ey = fmaxf(fabsf(ay - ((iy * kCellY) * resf + bhy)) - bhy, 0.f);
+                if (fmaf(ey, ey, exz) <= lim) cm |= 1u << (ix * (kTile / kCellY) + iy);
             }
         }
-    }
-
-    for (int L = 0; L < nl; ++L) {
-        uint32_t pos = __shfl_sync(0xffffffffu, my_off, L);
-        if (__shfl_sync(0xffffffffu, my_cnt, L) == 0) continue;
-        int lo, hi;
-        layer_z(L, lo, hi);
-        for (uint32_t i0 = 0; i0 < bin.y; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            const bool in = i < bin.y && ((lm(i) >> L) & 1u);
-            const uint32_t bal = __ballot_sync(0xffffffffu, in);
-            if (in) {
-                const size_t slot = pos + __popc(bal & ((1u << lane) - 1u));
-                const uint32_t n = P.lists[base + i];
-                const AtomRec rec = P.recs[n];
-                const float r = rec.r;
-                float r2hi, r2lo;
-                band_of(r, r2hi, r2lo);
-                const double rs = (double)r * P.sigma;
-                const float kc = (float)(-0.5 * 1.4426950408889634 / (rs * rs));
-                const float ax = (float)(rec.px - ox0), ay = (float)(rec.py - oy0), az = (float)(rec.pz + P.half_width);
-                // forbidden planes (block-cull emulation) are kept only where the cutoff sphere can reach them, so
-                // that most entries carry "none" and the voxelize kernels skip the cull arithmetic
-                const int fx = rec.fx - x0, fy = rec.fy - y0;
-                const float rr = r * 1.001f + 0.01f * resf;
-                const bool kx = rec.fx >= 0 && fx >= 0 && fx < kTile && fabsf(ax - fx * resf) <= rr;
-                const bool ky = rec.fy >= 0 && fy >= 0 && fy < kTile && fabsf(ay - fy * resf) <= rr;
-                const bool kz = rec.fz >= 0 && fabsf(az - rec.fz * resf) <= rr;
-                const uint32_t forb = (uint32_t)(kx ? fx : 0xFF) | ((uint32_t)(ky ? fy : 0xFF) << 8) |
-                                      ((uint32_t)(kz ? rec.fz : 0xFFFF) << 16);
-                // cells of this layer reached by the cutoff sphere: exact sphere / voxel-centre-box test
-                const float lim = r2hi + 1e-4f * (1.f + r2hi);
-                const float ez2 = layer_ez2(az, lo, hi);
-                uint32_t cm = 0u;
+        float4* e = P.lent + slot * (size_t)P.es4;
+        e[0] = make_float4(ax, ay, az, r2hi);
+        e[1] = make_float4(r2lo, kc, __uint_as_float(forb), P.mode == 1 ? __uint_as_float((uint32_t)P.types[n]) : r);
+        e[2] = make_float4(__uint_as_float(n), __uint_as_float(cm), 0.f, 0.f);
+        P.lmask[slot] = cm;
+        if (P.mode == 2) {
+            const float* f = P.features + (size_t)n * P.C;
+            const int nq = P.es4 - 3;
+            if ((P.C & 3) == 0) {
+                for (int k = 0; k < nq; ++k)
+                    e[3 + k] = 4 * k < P.C ? __ldg(reinterpret_cast<const float4*>(f) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (int k = 0; k < nq; ++k) {
+                    float v[4];
 #pragma unroll
-                for (int ix = 0; ix < kTile / kCellX; ++ix) {
-                    const float ex = fmaxf(fabsf(ax - ((ix * kCellX) * resf + bhx)) - bhx, 0.f);
-                    const float exz = fmaf(ex, ex, ez2);
-#pragma unroll
-                    for (int iy = 0; iy < kTile / kCellY; ++iy) {
-                        const float ey = fmaxf(fabsf(ay - ((iy * kCellY) * resf + bhy)) - bhy, 0.f);
-                        if (fmaf(ey, ey, exz) <= lim) cm |= 1u << (ix * (kTile / kCellY) + iy);
-                    }
-                }
-                float4* e = lent + slot * (size_t)P.es4;
-                e[0] = make_float4(ax, ay, az, r2hi);
-                e[1] = make_float4(r2lo, kc, __uint_as_float(forb),
-                                   P.mode == 1 ? __uint_as_float((uint32_t)P.types[n]) : r);
-                e[2] = make_float4(__uint_as_float(n), __uint_as_float(cm), 0.f, 0.f);
-                lmask[slot] = cm;
-                if (P.mode == 2) {
-                    const float* f = P.features + (size_t)n * P.C;
-                    const int nq = P.es4 - 3;
-                    if ((P.C & 3) == 0) {
-                        for (int q = 0; q < nq; ++q) e[3 + q] = __ldg(reinterpret_cast<const float4*>(f) + q);
-                    } else {
-                        for (int q = 0; q < nq; ++q) {
-                            float v[4];
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) v[c] = (4 * q + c < P.C) ? __ldg(f + 4 * q + c) : 0.f;
-                            e[3 + q] = make_float4(v[0], v[1], v[2], v[3]);
-                        }
-                    }
+                    for (int c = 0; c < 4; ++c) v[c] = (4 * k + c < P.C) ? __ldg(f + 4 * k + c) : 0.f;
+                    e[3 + k] = make_float4(v[0], v[1], v[2], v[3]);
                 }
             }
-            pos += __popc(bal);
         }
     }
 }
@@ -1215,7 +1279,7 @@ __device__ __forceinline__ void tiles_body(const VoxParams& P, const int tile_id
     }
     const int ES4 = P.es4;
     const int SC = min(kStageMaxEntries, stage_bytes<MODE>() / (ES4 * (int)sizeof(float4)));
-    const size_t colseg = ((size_t)P.mol_offsets[mol] * (size_t)P.maxcols + bin.x) * (size_t)P.zl + seg_start;
+    const size_t colseg = (size_t)P.mol_offsets[mol] * (size_t)P.maxcols * (size_t)P.zl + bin.x + seg_start;
     const float4* src = P.lent + colseg * (size_t)ES4;
     const uint32_t* msrc = P.lmask + colseg;
     const bool single_round = total <= SC;
