@@ -53,7 +53,7 @@ struct Plan {
     int form;        // voxelize kernel form, see enum Form
     int ncell;
     int nlayers, zl, es4;
-    size_t off_lent, off_lmask, off_lbins, off_tdesc, off_kcnt, off_lids;   // kcnt: key counts, then key cursors
+    size_t off_lent, off_lbins, off_tdesc, off_kcnt, off_lids;   // kcnt: key counts, then key cursors
     int pipe_sc;   // pipelined form: largest tile (entries) it takes
 };
 
@@ -205,7 +205,6 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
         pl->zl = zl;
         const size_t nle = layered(pl->form) ? N * (size_t)pl->maxcols * (size_t)zl : 0;
         pl->off_lent = off;  off += align_up(nle * (size_t)pl->es4 * 16);
-        pl->off_lmask = off; off += align_up(nle * sizeof(uint32_t));
         pl->off_lbins = off; off += align_up(layered(pl->form) ? B * (size_t)pl->ncol * (size_t)layers * sizeof(uint2) : 0);
         pl->off_tdesc = off; off += align_up(pl->form == FORM_PIPE ? B * (size_t)pl->ncol * (size_t)pl->nzc * sizeof(mvx::TileDesc) : 0);
         const size_t nkeys = layered(pl->form) ? B * (size_t)pl->ncol * (size_t)layers : 0;
@@ -408,7 +407,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         lp.recs = recs; lp.types = batch->types; lp.features = batch->features;
         lp.bins = bins; lp.lbins = (uint2*)(ws + pl.off_lbins);
         lp.tdesc = pl.form == FORM_PIPE ? (mvx::TileDesc*)(ws + pl.off_tdesc) : nullptr;
-        lp.lent = (float4*)(ws + pl.off_lent); lp.lmask = (uint32_t*)(ws + pl.off_lmask);
+        lp.lent = (float4*)(ws + pl.off_lent);
         const size_t nkeys = (size_t)B * pl.ncol * pl.nlayers;
         lp.N = N; lp.kcnt = (const uint32_t*)(ws + pl.off_kcnt); lp.cursor = (uint32_t*)(ws + pl.off_kcnt) + nkeys;
         lp.lids = (uint32_t*)(ws + pl.off_lids);
@@ -419,7 +418,9 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         if (N > 0) {
             mvx::mvx_lplace_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(lp);
             MVX_CUDA_OK(cudaGetLastError());
-            mvx::mvx_lbuild_kernel<<<(unsigned)((nkeys + 7) / 8), 256, 0, st>>>(lp);
+            static bool cfg_b = false;
+            if (!cfg_b) { MVX_CUDA_OK(set_smem(mvx::mvx_lbuild_kernel, mvx::lbuild_smem_bytes(mvx::kLBuildStageQ))); cfg_b = true; }
+            mvx::mvx_lbuild_kernel<<<(unsigned)((nkeys + 7) / 8), 256, mvx::lbuild_smem_bytes(pl.es4), st>>>(lp);
             MVX_CUDA_OK(cudaGetLastError());
         }
     } else {
@@ -460,7 +461,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         vp.types = batch->types; vp.features = batch->features; vp.chan_radii = nullptr; vp.out = out; vp.out_kind = batch->out_dtype;
         vp.entries = entries; vp.masks = legacy_masks;
         vp.nlayers = pl.nlayers; vp.zl = pl.zl; vp.es4 = pl.es4;
-        vp.lent = (const float4*)(ws + pl.off_lent); vp.lmask = (const uint32_t*)(ws + pl.off_lmask);
+        vp.lent = (const float4*)(ws + pl.off_lent);
         vp.lbins = (const uint2*)(ws + pl.off_lbins);
         vp.tdesc = pl.form == FORM_PIPE ? (const mvx::TileDesc*)(ws + pl.off_tdesc) : nullptr;
         vp.pipe_sc = pl.pipe_sc;

@@ -132,7 +132,6 @@ struct VoxParams {
     int masks;                 // 1: entries carry precomputed cell masks
     int nlayers, zl, es4;      // layered entries (see ExpandParams)
     const float4* lent;
-    const uint32_t* lmask;
     const uint2* lbins;
     const TileDesc* tdesc;     // pipelined form; for the tile form: non-null = only tiles with more than pipe_sc entries
     int pipe_sc;               // pipelined form: largest tile (entries) it takes; larger ones go to the tile form
@@ -492,7 +491,6 @@ struct LBinParams {
     uint2* lbins;       // per (molecule, column, layer): (offset in the column's segment, count)
     TileDesc* tdesc;    // per (molecule, column, z chunk), or nullptr
     float4* lent;       // molecule m owns entries [mol_offsets[m] * maxcols * zl, ...), es4 float4 words each
-    uint32_t* lmask;    // per layered entry: its 8-bit cell mask (tile form)
 };
 
 __global__ void __launch_bounds__(256) mvx_lscan_kernel(const LBinParams P) {
@@ -568,11 +566,16 @@ __global__ void __launch_bounds__(256) mvx_lplace_kernel(const LBinParams P) {
         }
 }
 
-constexpr int kLBuildIds = 256;   // ids of a segment ranked from shared memory per round
+constexpr int kLBuildIds = 256;     // ids of a segment ranked from shared memory per round
+constexpr int kLBuildStageQ = 12;   // float4 words per entry the coalescing stage holds (C <= 36 channels)
+inline size_t lbuild_smem_bytes(int es4) { return 8 * (2 * kLBuildIds * sizeof(uint32_t) + 32 * (size_t)(es4 <= kLBuildStageQ ? es4 : 0) * sizeof(float4)); }
 
 __global__ void __launch_bounds__(256) mvx_lbuild_kernel(const LBinParams P) {
-    __shared__ __align__(16) uint32_t s_ids[8][kLBuildIds];
+    extern __shared__ __align__(16) unsigned char s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* buf = reinterpret_cast<uint32_t*>(s_raw) + warp * 2 * kLBuildIds;   // the segment's ids as claimed
+    uint32_t* srt = buf + kLBuildIds;                                             // ... in ascending order
+    float4* stage = reinterpret_cast<float4*>(s_raw + 8 * 2 * kLBuildIds * sizeof(uint32_t)) + warp * 32 * P.es4;   // sized for es4 <= kLBuildStageQ
     const long long key = (long long)blockIdx.x * 8 + warp;
     if (key >= (long long)P.B * P.ncol * P.nl) return;
     const uint2 lb = P.lbins[key];
@@ -583,7 +586,7 @@ __global__ void __launch_bounds__(256) mvx_lbuild_kernel(const LBinParams P) {
     const int col = (int)(gcol % P.ncol), mol = (int)(gcol / P.ncol);
     const size_t seg = (size_t)P.mol_offsets[mol] * (size_t)P.maxcols * (size_t)P.zl + P.bins[gcol].x + lb.x;
     const uint32_t* ids = P.lids + seg;
-    uint32_t* buf = s_ids[warp];
+    const int ES4 = P.es4;
 
     const int x0 = (col / P.ncx) * kTile, y0 = (col % P.ncx) * kTile;
     const double ox0 = (double)x0 * P.res - P.half_width, oy0 = (double)y0 * P.res - P.half_width;
@@ -596,27 +599,8 @@ __global__ void __launch_bounds__(256) mvx_lbuild_kernel(const LBinParams P) {
     const float bhz = 0.5f * (zhi - zlo - 1) * resf;
     const float zmid = zlo * resf + bhz;
 
-    for (int i0 = 0; i0 < S; i0 += 32) {   // 32 entries per round, one per lane
-        const int i = i0 + lane;
-        const uint32_t n = i < S ? ids[i] : 0xFFFFFFFFu;
-        // rank = ids of the segment smaller than mine (ids are distinct): the entry's place in ascending atom order
-        uint32_t rank = 0;
-        for (int j0 = 0; j0 < S; j0 += kLBuildIds) {
-            const int nj = min(kLBuildIds, S - j0);
-            if (S > kLBuildIds || i0 == 0) {   // a segment that fits is staged once
-                __syncwarp();
-                for (int j = lane; j < nj; j += 32) buf[j] = ids[j0 + j];
-                __syncwarp();
-            }
-            int j = 0;
-            for (; j + 4 <= nj; j += 4) {
-                const uint4 v = *reinterpret_cast<const uint4*>(buf + j);
-                rank += (v.x < n) + (v.y < n) + (v.z < n) + (v.w < n);
-            }
-            for (; j < nj; ++j) rank += buf[j] < n;
-        }
-        if (i >= S) continue;
-        const size_t slot = seg + rank;
+    // words 0..2 of atom n's entry and its 8-bit cell mask
+    auto make_entry = [&](const uint32_t n, float4& e0, float4& e1, float4& e2) -> uint32_t {
         const AtomRec rec = P.recs[n];
         const float r = rec.r;
         const float r2 = r * r;
@@ -649,25 +633,86 @@ __global__ void __launch_bounds__(256) mvx_lbuild_kernel(const LBinParams P) {
                 if (fmaf(ey, ey, exz) <= lim) cm |= 1u << (ix * (kTile / kCellY) + iy);
             }
         }
-        float4* e = P.lent + slot * (size_t)P.es4;
-        e[0] = make_float4(ax, ay, az, r2hi);
-        e[1] = make_float4(r2lo, kc, __uint_as_float(forb), P.mode == 1 ? __uint_as_float((uint32_t)P.types[n]) : r);
-        e[2] = make_float4(__uint_as_float(n), __uint_as_float(cm), 0.f, 0.f);
-        P.lmask[slot] = cm;
-        if (P.mode == 2) {
-            const float* f = P.features + (size_t)n * P.C;
-            const int nq = P.es4 - 3;
-            if ((P.C & 3) == 0) {
-                for (int k = 0; k < nq; ++k)
-                    e[3 + k] = 4 * k < P.C ? __ldg(reinterpret_cast<const float4*>(f) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-                for (int k = 0; k < nq; ++k) {
-                    float v[4];
+        e0 = make_float4(ax, ay, az, r2hi);
+        e1 = make_float4(r2lo, kc, __uint_as_float(forb), P.mode == 1 ? __uint_as_float((uint32_t)P.types[n]) : r);
+        e2 = make_float4(__uint_as_float(n), __uint_as_float(cm), 0.f, 0.f);
+        return cm;
+    };
+    auto feature_word = [&](const float* f, const int k) -> float4 {   // word k of the padded feature row
+        if ((P.C & 3) == 0) return 4 * k < P.C ? __ldg(reinterpret_cast<const float4*>(f) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float v[4];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) v[c] = (4 * k + c < P.C) ? __ldg(f + 4 * k + c) : 0.f;
-                    e[3 + k] = make_float4(v[0], v[1], v[2], v[3]);
+        for (int c = 0; c < 4; ++c) v[c] = (4 * k + c < P.C) ? __ldg(f + 4 * k + c) : 0.f;
+        return make_float4(v[0], v[1], v[2], v[3]);
+    };
+
+    if (S <= kLBuildIds && ES4 <= kLBuildStageQ) {
+        // common case.  rank = ids of the segment smaller than mine (ids are distinct) = the entry's place in
+        // ascending atom order; sorted ids go to shared memory, then each round builds 32 CONSECUTIVE entries in
+        // the stage and copies them out as one contiguous, fully coalesced block
+        for (int j = lane; j < S; j += 32) buf[j] = ids[j];
+        __syncwarp();
+        for (int i = lane; i < S; i += 32) {
+            const uint32_t n = buf[i];
+            uint32_t rank = 0;
+            int j = 0;
+            for (; j + 4 <= S; j += 4) {
+                const uint4 v = *reinterpret_cast<const uint4*>(buf + j);
+                rank += (v.x < n) + (v.y < n) + (v.z < n) + (v.w < n);
+            }
+            for (; j < S; ++j) rank += buf[j] < n;
+            srt[rank] = n;
+        }
+        __syncwarp();
+        for (int i0 = 0; i0 < S; i0 += 32) {
+            const int i = i0 + lane, nv = min(32, S - i0);
+            if (i < S) {
+                const uint32_t n = srt[i];
+                float4 e0, e1, e2;
+                make_entry(n, e0, e1, e2);
+                float4* e = stage + lane * ES4;
+                e[0] = e0; e[1] = e1; e[2] = e2;
+                if (P.mode == 2) {
+                    const float* f = P.features + (size_t)n * P.C;
+                    for (int k = 0; k < ES4 - 3; ++k) e[3 + k] = feature_word(f, k);
                 }
             }
+            __syncwarp();
+            float4* dst = P.lent + (seg + i0) * (size_t)ES4;
+            for (int q = lane; q < nv * ES4; q += 32) dst[q] = stage[q];
+            __syncwarp();
+        }
+        return;
+    }
+
+    // large segments / wide feature rows: ids ranked in rounds from shared memory, entries stored in place
+    for (int i0 = 0; i0 < S; i0 += 32) {   // 32 entries per round, one per lane
+        const int i = i0 + lane;
+        const uint32_t n = i < S ? ids[i] : 0xFFFFFFFFu;
+        uint32_t rank = 0;
+        for (int j0 = 0; j0 < S; j0 += kLBuildIds) {
+            const int nj = min(kLBuildIds, S - j0);
+            if (S > kLBuildIds || i0 == 0) {   // a segment that fits is staged once
+                __syncwarp();
+                for (int j = lane; j < nj; j += 32) buf[j] = ids[j0 + j];
+                __syncwarp();
+            }
+            int j = 0;
+            for (; j + 4 <= nj; j += 4) {
+                const uint4 v = *reinterpret_cast<const uint4*>(buf + j);
+                rank += (v.x < n) + (v.y < n) + (v.z < n) + (v.w < n);
+            }
+            for (; j < nj; ++j) rank += buf[j] < n;
+        }
+        if (i >= S) continue;
+        const size_t slot = seg + rank;
+        float4 e0, e1, e2;
+        make_entry(n, e0, e1, e2);
+        float4* e = P.lent + slot * (size_t)ES4;
+        e[0] = e0; e[1] = e1; e[2] = e2;
+        if (P.mode == 2) {
+            const float* f = P.features + (size_t)n * P.C;
+            for (int k = 0; k < ES4 - 3; ++k) e[3 + k] = feature_word(f, k);
         }
     }
 }
@@ -1281,7 +1326,6 @@ __device__ __forceinline__ void tiles_body(const VoxParams& P, const int tile_id
     const int SC = min(kStageMaxEntries, stage_bytes<MODE>() / (ES4 * (int)sizeof(float4)));
     const size_t colseg = (size_t)P.mol_offsets[mol] * (size_t)P.maxcols * (size_t)P.zl + bin.x + seg_start;
     const float4* src = P.lent + colseg * (size_t)ES4;
-    const uint32_t* msrc = P.lmask + colseg;
     const bool single_round = total <= SC;
     bool staged = false;
 
@@ -1323,7 +1367,7 @@ __device__ __forceinline__ void tiles_body(const VoxParams& P, const int tile_id
                     const float4* g = src + (size_t)r0 * ES4;
                     const int nq = nc * ES4;
                     for (int q = tid; q < nq; q += kThreads) sE[q] = g[q];
-                    for (int i = tid; i < nc; i += kThreads) sM[i] = msrc[r0 + i];
+                    for (int i = tid; i < nc; i += kThreads) sM[i] = __float_as_uint(g[(size_t)i * ES4 + 2].y);   // cell mask, word 2 of the entry
                     __syncthreads();
                     if (MODE == 2 && P.chan_radii != nullptr) {   // channel-wise features: this channel's radius
                         const float r = P.chan_radii[c0];
