@@ -111,6 +111,7 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     mvx::Geo& g = pl->geo;
     const int D = s->dimension;
     g.res = s->resolution;
+    g.inv_res = 1.0 / s->resolution;
     const double width = s->resolution * (double)(D - 1);   // base/voxelizer.py:28
     g.half_width = width / 2.0;                            // numpy/voxelizer.py:42
     g.res_half = s->resolution / 2.0;                      // :55
@@ -413,7 +414,9 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         lp.lids = (uint32_t*)(ws + pl.off_lids);
         if ((nkeys + 7) / 8 > 0x7fffffffULL) return fail(MVX_ERR_BAD_SHAPE, "batch too large for one launch; split it");
         const size_t smem = 2 * (size_t)pl.ncol * sizeof(uint32_t);
-        mvx::mvx_lscan_kernel<<<(unsigned)B, 256, smem, st>>>(lp);
+        int sgroups = (pl.ncol + 7) / 8;   // small batches: spread each molecule's output over several CTAs
+        if ((long long)B * sgroups > 1184) sgroups = (int)std::fmax(1.0, 1184.0 / B);
+        mvx::mvx_lscan_kernel<<<(unsigned)(B * sgroups), 256, smem, st>>>(lp, sgroups);
         MVX_CUDA_OK(cudaGetLastError());
         if (N > 0) {
             mvx::mvx_lplace_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(lp);

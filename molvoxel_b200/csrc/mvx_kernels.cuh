@@ -38,7 +38,7 @@ struct __align__(8) AtomRec {
 static_assert(sizeof(AtomRec) == 40, "AtomRec layout");
 
 struct Geo {
-    double res, half_width, res_half, lower, upper;
+    double res, inv_res, half_width, res_half, lower, upper;
     double clip_lo, clip_hi;     // scalar-form clip thresholds (lower - r, upper + r)
     double size_scalar;          // scalar-form atom_size for the cull
     double sigma;
@@ -223,8 +223,8 @@ __global__ void __launch_bounds__(256) mvx_prep_kernel(const PrepParams P) {
     int v0[3], v1[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        double t0 = floor((p[k] - reach + g.half_width) / g.res - 0.01);
-        double t1 = ceil((p[k] + reach + g.half_width) / g.res + 0.01);
+        double t0 = floor((p[k] - reach + g.half_width) * g.inv_res - 0.01);
+        double t1 = ceil((p[k] + reach + g.half_width) * g.inv_res + 0.01);
         t0 = t0 < 0.0 ? 0.0 : t0;
         t1 = t1 > (double)(g.dim - 1) ? (double)(g.dim - 1) : t1;
         if (!(t0 <= t1)) keep = false;   // also catches NaN
@@ -493,25 +493,25 @@ struct LBinParams {
     float4* lent;       // molecule m owns entries [mol_offsets[m] * maxcols * zl, ...), es4 float4 words each
 };
 
-__global__ void __launch_bounds__(256) mvx_lscan_kernel(const LBinParams P) {
+__global__ void __launch_bounds__(256) mvx_lscan_kernel(const LBinParams P, const int groups) {
     extern __shared__ uint32_t s_u32[];
     uint32_t* s_cnt = s_u32;            // [ncol] layered totals of the molecule's columns
     uint32_t* s_off = s_u32 + P.ncol;   // [ncol] their exclusive prefix sums
-    const int mol = blockIdx.x;
+    const int mol = blockIdx.x / groups, grp = blockIdx.x % groups;   // every CTA of a molecule scans all its columns, writes its share
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int nl = P.nl;
     const int ncz_max = (P.tz + kCellZ - 1) / kCellZ;
     const size_t lseg = (size_t)P.mol_offsets[mol] * (size_t)P.maxcols * (size_t)P.zl;
-    for (int col = warp; col < P.ncol; col += nwarps) {
-        const size_t gcol = (size_t)mol * P.ncol + col;
-        const uint32_t c = lane < nl ? P.kcnt[gcol * nl + lane] : 0u;
-        const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
-        if (lane == 0) s_cnt[col] = tot;
+    for (int col = threadIdx.x; col < P.ncol; col += blockDim.x) {
+        const uint32_t* k = P.kcnt + ((size_t)mol * P.ncol + col) * nl;
+        uint32_t tot = 0;
+        for (int L = 0; L < nl; ++L) tot += k[L];
+        s_cnt[col] = tot;
     }
     __syncthreads();
     if (warp == 0) bin_scan_counts(s_cnt, s_off, P.ncol, lane);
     __syncthreads();
-    for (int col = warp; col < P.ncol; col += nwarps) {
+    for (int col = grp * nwarps + warp; col < P.ncol; col += groups * nwarps) {
         const size_t gcol = (size_t)mol * P.ncol + col;
         const uint32_t my_cnt = lane < nl ? P.kcnt[gcol * nl + lane] : 0u;
         uint32_t xs = my_cnt;

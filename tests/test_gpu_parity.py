@@ -519,3 +519,31 @@ def test_pipelined_form_overflow_tiles_vs_oracle(monkeypatch):
     ref = oracle_forward_batch(0.5, 40, "scalar", "binary", 0.5, 8, "features", offs, coords, None, None, feats, 20, 1.0,
                                num_threads=8)
     assert np.array_equal(out, ref)
+
+
+def test_collated_point_clouds_through_the_pipelined_host_path():
+    """Row f2 end to end: point clouds (atoms + bond midpoints, ligand/protein channel offsets) -> pinned CSR
+    collation -> non_blocking forward_types_batch, against the oracle on the same collated arrays."""
+    from molvoxel_b200.pointcloud import Collator, system_point_cloud
+    rng = np.random.default_rng(77)
+    col = Collator(pinned=True)
+    vox = mv.create_voxelizer(0.5, 32, "atom-wise", "gaussian", library="b200")
+    outs, refs = [], []
+    for step in range(3):
+        clouds = []
+        for _ in range(5):
+            na, nprot = int(rng.integers(8, 20)), int(rng.integers(20, 60))
+            lig = dict(atom_coords=rng.normal(scale=2.0, size=(na, 3)), atom_channels=rng.integers(0, 4, size=na), num_atom_channels=4,
+                       bonds=rng.integers(0, na, size=(na, 2)), bond_channels=rng.integers(0, 3, size=na), num_bond_channels=3)
+            prot = dict(atom_coords=rng.normal(scale=5.0, size=(nprot, 3)), atom_channels=rng.integers(0, 5, size=nprot), num_atom_channels=5)
+            clouds.append(system_point_cloud([lig, prot], "types"))
+        radii = [rng.uniform(0.8, 1.6, size=c.coords.shape[0]).astype(np.float32) for c in clouds]
+        b = col(clouds, centers="mean", radii=radii)
+        outs.append(vox.forward_types_batch(b["coords"], b["mol_offsets"], b["centers"], b["channels"], b["radii"],
+                                            b["num_channels"], non_blocking=True).clone())
+        refs.append(oracle_forward_batch(0.5, 32, "atom-wise", "gaussian", 0.5, 8, "types", b["mol_offsets"].copy(),
+                                         b["coords"].copy(), b["centers"].copy(), b["channels"].copy(), None, 12,
+                                         b["radii"].copy(), num_threads=8))
+    vox.check_status()
+    for o, r in zip(outs, refs):
+        _compare(o.cpu().numpy(), r, False)
