@@ -375,6 +375,48 @@ def run_b200_arm(args):
     ms_e2e_blocking, _, _ = timed(step_host_blocking, min(K, 50))
     ms_e2e_blocking *= K / min(K, 50)
 
+    # The same pipelined host path with the finished grids also copied back to pinned HOST memory every step
+    # (what a host-side consumer would see).  Bounded: a slice of the batch, a few steps — it measures PCIe.
+    Bd = max(1, min(B, int(2e9 // (esize * C * D ** 3))))
+    Kd = max(3, min(K, 10))
+    offs_d2h = np.ascontiguousarray(batch["offs"][:Bd + 1])
+    nd = int(offs_d2h[-1])
+    host_grid = torch.empty((2, Bd, C, D, D, D), dtype=out_dt).pin_memory()
+    d2h_stream = torch.cuda.Stream(dev)
+    d2h_done = [torch.cuda.Event(), torch.cuda.Event()]
+    h_small = {"offs": pin(offs_d2h)[0], "coords": h["coords"][:nd], "centers": h["centers"][:Bd], "chan": h["chan"][:nd],
+               "radii": h["radii"] if np.isscalar(h["radii"]) else h["radii"][:nd]}
+    ring_d = [ring[0][:Bd], ring[1][:Bd]]
+
+    def step_host_d2h(k):
+        d2h_done[k & 1].synchronize()   # the host slot of step k-2 has been read back
+        vox._forward_batch(w["mode"], h_small["coords"], h_small["offs"], h_small["centers"], h_small["chan"], h_small["radii"],
+                           C, 0.0, False, ring_d[k & 1], max_radius=max_r, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(ev)
+            host_grid[k & 1].copy_(ring_d[k & 1], non_blocking=True)
+            d2h_done[k & 1].record(d2h_stream)
+
+    def timed_d2h():
+        for k in range(2):
+            step_host_d2h(k)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(Kd):
+            step_host_d2h(k)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+    try:
+        sec_d2h = timed_d2h()
+        vox.check_status()
+        d2h_info = {"value": world * Bd * Kd / sec_d2h, "batch": Bd, "steps": Kd, "d2h_bytes_per_step": int(Bd * esize * C * D ** 3),
+                    "note": "same pipelined host path + the finished grids copied to pinned host memory every step (separate D2H stream, 2 host slots); bounded slice of the batch, wall clock with a final synchronize — PCIe-bound"}
+    except Exception as e:   # a reported extra; never fail the bench because of it
+        d2h_info = {"error": repr(e)[:200]}
+    del host_grid
+
     launches = _lib.lib().mvx_launches_per_call  # per-call count from the library itself
     import ctypes
     spec = vox._spec()
@@ -385,6 +427,7 @@ def run_b200_arm(args):
     bb.mol_offsets = bb.coords = bb.types = bb.features = bb.radii = dummy
     bb.radius, bb.max_radius = 1.0, 2.0
     per_call = launches(ctypes.byref(spec), ctypes.byref(bb))
+    kernel_name = _lib.FORM_KERNEL.get(_lib.lib().mvx_voxelize_form(ctypes.byref(spec), ctypes.byref(bb)), "mvx_voxelize_kernel")
 
     if rank != 0:
         if world > 1:
@@ -410,14 +453,16 @@ def run_b200_arm(args):
         "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / K,
                 "blocking_value": mols / (ms_e2e_blocking * 1e-3),
+                "with_grid_d2h": d2h_info,
                 "note": "public Voxelizer API with pinned HOST inputs, every step: async H2D (copy stream, 2-deep staging ring) -> prep/bin/voxelize -> D2H of the status word; one sync at the end of the timed region. blocking_value = mvx_voxelize_host (one sync per call). Grids stay in HBM (reference torch-backend convention)"},
         "gpu_launches": per_call * K,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "mvx_voxelize_kernel", "kernel_ms": prof["vox"],
+                     "traffic": traffic, "kernel": kernel_name, "kernel_ms": prof["vox"],
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "write_only_reference_gbs": fill_gbs,
                      "note": "peak is the measured COPY bandwidth (read+write); this kernel only writes, so frac can exceed 1.0 — write_only_reference_gbs is torch zero_() (device memset) on the same buffers",
-                     "step_share": {"prep_ms": prof["prep"], "bin_ms": prof["bin"], "voxelize_ms": prof["vox"]}},
+                     "step_share": {"prep_ms": prof["prep"], "bin_ms": prof["bin"], "voxelize_ms": prof["vox"],
+                                    "note": "bin_ms = column/layer binning + entry build kernels between prep and voxelize"}},
         "clocks": clocks,
     }
     if world == 1:   # the reference's own calling pattern: one molecule per call, host arrays in (cfg 1 shape)

@@ -118,6 +118,10 @@ int mvx_check_status(void *workspace, void *stream);
 /* Number of kernels one mvx_voxelize call launches for this spec/batch (bench.py's gpu_launches). */
 int mvx_launches_per_call(const mvx_grid_spec *spec, const mvx_batch *batch);
 
+/* Which voxelize kernel form mvx_voxelize picks for this spec/batch (by atom density; all forms give the same
+ * results): 0 generic rows, 1 warp cells (ligand batches), 3 tiles, 4 pipelined persistent form (dense batches). */
+int mvx_voxelize_form(const mvx_grid_spec *spec, const mvx_batch *batch);
+
 /*
  * Per-kernel device timing for bench.py's roofline: between begin and end every mvx_voxelize call on
  * this thread records CUDA events around its launches on the caller's stream (no synchronisation until

@@ -28,6 +28,7 @@ MVX_F32, MVX_F64 = 0, 1
 DENSITY = {"gaussian": 0, "binary": 1}
 RADII = {"scalar": 0, "channel-wise": 1, "atom-wise": 2}
 MODE = {"single": 0, "types": 1, "features": 2}
+FORM_KERNEL = {0: "mvx_voxelize_kernel", 1: "mvx_voxelize_cells_kernel", 3: "mvx_voxelize_tiles_kernel", 4: "mvx_voxelize_pipe_kernel"}
 OUT_DTYPE = {"float32": 0, "bfloat16": 1, "float16": 2}
 
 
@@ -106,12 +107,13 @@ def lib():
         L.mvx_voxelize_host.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch), vp, vp, sz, vp]
         L.mvx_check_status.argtypes = [vp, vp]
         L.mvx_launches_per_call.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch)]
+        L.mvx_voxelize_form.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch)]
         L.mvx_profile_begin.argtypes = [ctypes.c_int]
         dp = ctypes.POINTER(ctypes.c_double)
         L.mvx_profile_end.argtypes = [dp, dp, dp, ctypes.POINTER(ctypes.c_int)]
         L.mvx_profile_begin.restype = L.mvx_profile_end.restype = ctypes.c_int
         for fn in (L.mvx_workspace_bytes, L.mvx_host_staging_bytes, L.mvx_voxelize, L.mvx_voxelize_host,
-                   L.mvx_check_status, L.mvx_launches_per_call):
+                   L.mvx_check_status, L.mvx_launches_per_call, L.mvx_voxelize_form):
             fn.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -119,7 +121,8 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "mvx_version", "mvx_last_error", "mvx_workspace_bytes", "mvx_host_staging_bytes", "mvx_voxelize",
-    "mvx_voxelize_host", "mvx_check_status", "mvx_launches_per_call", "mvx_profile_begin", "mvx_profile_end",
+    "mvx_voxelize_host", "mvx_check_status", "mvx_launches_per_call", "mvx_voxelize_form", "mvx_profile_begin",
+    "mvx_profile_end",
 ]
 
 

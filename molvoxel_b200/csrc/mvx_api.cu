@@ -352,6 +352,12 @@ int mvx_launches_per_call(const mvx_grid_spec* spec, const mvx_batch* batch) {
     return (batch->total_atoms > 0 ? 1 : 0) + nbin + nexp + nvox * (pl.form == FORM_PIPE ? 2 : 1);   // prep + bin + expand + voxelize
 }
 
+int mvx_voxelize_form(const mvx_grid_spec* spec, const mvx_batch* batch) {
+    Plan pl;
+    int rc = make_plan(spec, batch, &pl);
+    return rc != MVX_OK ? rc : pl.form;
+}
+
 int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, void* workspace,
                  size_t workspace_bytes, void* stream) {
     Plan pl;

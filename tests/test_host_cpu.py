@@ -41,6 +41,24 @@ def test_workspace_planning_is_host_only():
     # 40 B record + 4 B column range + 4 columns x 4 B list entries per atom, 8 B per (molecule, column) bin
     assert need.value >= 100_000 * (40 + 4 + 16 + 4 * 48) + 2048 * 64 * 8
     assert L.mvx_launches_per_call(ctypes.byref(spec), ctypes.byref(b)) == 4   # prep, bin, expand, voxelize
+    assert L.mvx_voxelize_form(ctypes.byref(spec), ctypes.byref(b)) == 1        # ligand batch: warp-cell form
+
+
+def test_kernel_form_follows_atom_density(monkeypatch):
+    """Dense batches (>= 64 expected atoms per 8x8 column) take the pipelined persistent form with its layered
+    counting-sort binning (prep, scan, place, build, voxelize, overflow sweep); D % 4 != 0 takes the generic form."""
+    monkeypatch.delenv("MVX_KERNEL", raising=False)
+    L = _lib.lib()
+    form = lambda dim, N, B, mode="features", C=16: L.mvx_voxelize_form(   # noqa: E731
+        ctypes.byref(_lib.GridSpec(0.5, dim, 0, 0.5, 0, 8)), ctypes.byref(_batch(mode, B, N, C, C)))
+    assert form(48, 256 * 2000, 256) == 4
+    assert form(48, 256 * 300, 256) == 1
+    assert form(64, 1024 * 50, 1024, "types", 9) == 1
+    assert form(50, 8 * 3000, 8) == 0
+    spec, b = _lib.GridSpec(0.5, 48, 0, 0.5, 0, 8), _batch("features", 256, 256 * 2000, 16, 16)
+    assert L.mvx_launches_per_call(ctypes.byref(spec), ctypes.byref(b)) == 6
+    monkeypatch.setenv("MVX_KERNEL", "tiles")
+    assert L.mvx_voxelize_form(ctypes.byref(spec), ctypes.byref(b)) == 3
 
 
 @pytest.mark.parametrize("mutate, code", [
