@@ -220,21 +220,40 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     return MVX_OK;
 }
 
+// The dynamic shared-memory limit is a per-device function attribute: remember which devices have it (the kernels are
+// template instantiations, so one DeviceSet per call site).
+struct DeviceSet {
+    unsigned long long bits[4] = {0, 0, 0, 0};   // devices 0..255
+    bool test_and_set(int dev) {
+        if (dev < 0 || dev > 255) return false;
+        const bool had = (bits[dev >> 6] >> (dev & 63)) & 1ull;
+        bits[dev >> 6] |= 1ull << (dev & 63);
+        return had;
+    }
+};
+
 template <typename K>
-cudaError_t set_smem(K kernel, size_t smem) {
+cudaError_t set_smem(K kernel, size_t smem, DeviceSet* done = nullptr) {
+    if (done != nullptr) {
+        int dev = -1;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (done->test_and_set(dev)) return cudaSuccess;
+    }
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 // CTAs of the persistent form: one per SM of the current device
 int pipe_grid(unsigned ntiles, unsigned* grid) {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
-            return -1;
-        sms = n;
+    static int sms[256] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 255) return -1;
+    if (sms[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) return -1;
+        sms[dev] = n;
     }
-    const unsigned want = (unsigned)sms;
+    const unsigned want = (unsigned)sms[dev];
     *grid = ntiles < want ? ntiles : want;
     return 0;
 }
@@ -243,8 +262,8 @@ template <int MODE, int CH, bool BINARY, bool O16>
 cudaError_t launch_form_out(const mvx::VoxParams& vp, int form, int nv, unsigned grid, cudaStream_t st) {
     if (form == FORM_PIPE) {
         constexpr size_t smem = mvx::kPipeSmemBytes;
-        static bool cfg = false, cfg_t = false;
-        if (!cfg) { cudaError_t e = set_smem(mvx::mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16>, smem); if (e != cudaSuccess) return e; cfg = true; }
+        static DeviceSet cfg, cfg_t;
+        { cudaError_t e = set_smem(mvx::mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16>, smem, &cfg); if (e != cudaSuccess) return e; }
         unsigned pg = 0;
         if (pipe_grid(grid, &pg) != 0) return cudaErrorInvalidDevice;
         mvx::mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16><<<pg, mvx::kPipeThreads, smem, st>>>(vp, grid);
@@ -252,17 +271,18 @@ cudaError_t launch_form_out(const mvx::VoxParams& vp, int form, int nv, unsigned
         if (e != cudaSuccess) return e;
         // tiles with more entries than the pipelined form takes (usually none): a small scanning grid
         constexpr size_t smem_t = mvx::tiles_smem_bytes<MODE>();
-        if (!cfg_t) { e = set_smem(mvx::mvx_voxelize_sweep_kernel<MODE, CH, BINARY, O16>, smem_t); if (e != cudaSuccess) return e; cfg_t = true; }
+        e = set_smem(mvx::mvx_voxelize_sweep_kernel<MODE, CH, BINARY, O16>, smem_t, &cfg_t);
+        if (e != cudaSuccess) return e;
         mvx::mvx_voxelize_sweep_kernel<MODE, CH, BINARY, O16><<<2 * pg < grid ? 2 * pg : grid, mvx::kThreads, smem_t, st>>>(vp, grid);
     } else if (form == FORM_TILES) {
         constexpr size_t smem = mvx::tiles_smem_bytes<MODE>();
-        static bool cfg = false;
-        if (!cfg) { cudaError_t e = set_smem(mvx::mvx_voxelize_tiles_kernel<MODE, CH, BINARY, O16>, smem); if (e != cudaSuccess) return e; cfg = true; }
+        static DeviceSet cfg;
+        { cudaError_t e = set_smem(mvx::mvx_voxelize_tiles_kernel<MODE, CH, BINARY, O16>, smem, &cfg); if (e != cudaSuccess) return e; }
         mvx::mvx_voxelize_tiles_kernel<MODE, CH, BINARY, O16><<<grid, mvx::kThreads, smem, st>>>(vp);
     } else if (form == FORM_CELLS) {
         constexpr size_t smem = mvx::cells_smem_bytes<MODE, CH>();
-        static bool cfg = false;
-        if (!cfg) { cudaError_t e = set_smem(mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, O16>, smem); if (e != cudaSuccess) return e; cfg = true; }
+        static DeviceSet cfg;
+        { cudaError_t e = set_smem(mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, O16>, smem, &cfg); if (e != cudaSuccess) return e; }
         mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, O16><<<grid, mvx::kThreads, smem, st>>>(vp);
     } else if (nv == 4) {
         mvx::mvx_voxelize_kernel<MODE, CH, BINARY, 4, O16><<<grid, mvx::kThreads, 0, st>>>(vp);
@@ -427,8 +447,8 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         if (N > 0) {
             mvx::mvx_lplace_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(lp);
             MVX_CUDA_OK(cudaGetLastError());
-            static bool cfg_b = false;
-            if (!cfg_b) { MVX_CUDA_OK(set_smem(mvx::mvx_lbuild_kernel, mvx::lbuild_smem_bytes(mvx::kLBuildStageQ))); cfg_b = true; }
+            static DeviceSet cfg_b;
+            MVX_CUDA_OK(set_smem(mvx::mvx_lbuild_kernel, mvx::lbuild_smem_bytes(mvx::kLBuildStageQ), &cfg_b));
             mvx::mvx_lbuild_kernel<<<(unsigned)((nkeys + 7) / 8), 256, mvx::lbuild_smem_bytes(pl.es4), st>>>(lp);
             MVX_CUDA_OK(cudaGetLastError());
         }

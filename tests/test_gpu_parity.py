@@ -547,3 +547,28 @@ def test_collated_point_clouds_through_the_pipelined_host_path():
     vox.check_status()
     for o, r in zip(outs, refs):
         _compare(o.cpu().numpy(), r, False)
+
+
+def test_size_independent_properties_full_dense_batch():
+    """Full cfg 2 batch (256 pockets x 2,000 atoms, C=16, 48^3) through the default (pipelined) form: properties that
+    need no oracle — determinism, batch element == single call, translation invariance, types == one-hot features."""
+    rng = np.random.default_rng(44)
+    B, V, C = 256, 2000, 16
+    half = 0.5 * 47 / 2
+    coords = rng.uniform(-half, half, size=(B * V, 3)).astype(np.float32).astype(np.float64)
+    offs = np.arange(B + 1, dtype=np.int32) * V
+    types = rng.integers(0, C, size=B * V).astype(np.int32)
+    feats = np.zeros((B * V, C), dtype=np.float32)
+    feats[np.arange(B * V), types] = 1.0
+    vox = mv.create_voxelizer(0.5, 48, "scalar", "gaussian", library="b200")
+    out = vox.forward_features_batch(coords, offs, None, feats, 1.0)
+    assert torch.equal(out, vox.forward_features_batch(coords, offs, None, feats, 1.0))          # same call, same bits
+    assert torch.equal(out, vox.forward_types_batch(coords, offs, None, types, 1.0, C))          # one-hot features == types
+    shift = np.array([2.0, -1.5, 4.25])
+    out2 = vox.forward_features_batch(coords + shift, offs, np.tile(shift, (B, 1)), feats, 1.0)
+    assert torch.equal(out, out2)
+    for m in (0, 101, 255):                                                                     # batch element == single call
+        a, b = offs[m], offs[m + 1]
+        assert torch.equal(vox.forward_features(coords[a:b], None, feats[a:b], 1.0), out[m])
+    mass = out.sum(dim=(1, 2, 3, 4)).cpu().numpy()
+    assert (mass > 0.5 * V).all() and np.isfinite(mass).all()
