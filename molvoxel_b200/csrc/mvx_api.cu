@@ -55,6 +55,8 @@ struct Plan {
     int nlayers, zl, es4;
     size_t off_lent, off_lbins, off_tdesc, off_kcnt, off_lids;   // kcnt: key counts, then key cursors
     int pipe_sc;   // pipelined form: largest tile (entries) it takes
+    int pipe_q;    // ... float4 words of its shared-memory ring
+    bool pipe_multi;   // ... with the hit-weight cache (several channel chunks per cell)
 };
 
 int check_args(const mvx_grid_spec* s, const mvx_batch* b) {
@@ -211,7 +213,10 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
         const size_t nkeys = layered(pl->form) ? B * (size_t)pl->ncol * (size_t)layers : 0;
         pl->off_kcnt = off;  off += align_up(2 * nkeys * sizeof(uint32_t));
         pl->off_lids = off;  off += align_up(nle * sizeof(uint32_t));
-        pl->pipe_sc = mvx::kPipeRingQ / 2 / pl->es4;   // the pipelined form takes tiles up to half its ring
+        // several channel chunks per cell: the pipelined kernel caches the hit weights, its ring is smaller
+        pl->pipe_multi = pick_chunk(b->mode, b->out_channels) == 16 && b->out_channels > 16;
+        pl->pipe_q = mvx::pipe_ring_q(pl->pipe_multi);
+        pl->pipe_sc = pl->pipe_q / 2 / pl->es4;   // the pipelined form takes tiles up to half its ring
     }
     pl->off_alayers = off;  off += align_up(layered(pl->form) ? N * sizeof(uint32_t) : 0);
     pl->off_lists = off;    off += align_up(layered(pl->form) ? 0 : N * (size_t)pl->maxcols * sizeof(uint32_t));
@@ -262,11 +267,21 @@ template <int MODE, int CH, bool BINARY, bool O16>
 cudaError_t launch_form_out(const mvx::VoxParams& vp, int form, int nv, unsigned grid, cudaStream_t st) {
     if (form == FORM_PIPE) {
         constexpr size_t smem = mvx::kPipeSmemBytes;
-        static DeviceSet cfg, cfg_t;
-        { cudaError_t e = set_smem(mvx::mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16>, smem, &cfg); if (e != cudaSuccess) return e; }
+        static DeviceSet cfg, cfg_m, cfg_t;
         unsigned pg = 0;
         if (pipe_grid(grid, &pg) != 0) return cudaErrorInvalidDevice;
-        mvx::mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16><<<pg, mvx::kPipeThreads, smem, st>>>(vp, grid);
+        if constexpr (CH == 16) {   // several channel chunks per cell (C > 16): hit-weight cache
+            if (vp.pipe_q == mvx::pipe_ring_q(true)) {
+                cudaError_t em = set_smem(mvx::mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, true>, smem, &cfg_m);
+                if (em != cudaSuccess) return em;
+                mvx::mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, true><<<pg, mvx::kPipeThreads, smem, st>>>(vp, grid);
+            }
+        }
+        if (CH != 16 || vp.pipe_q != mvx::pipe_ring_q(true)) {
+            cudaError_t em = set_smem(mvx::mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, false>, smem, &cfg);
+            if (em != cudaSuccess) return em;
+            mvx::mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, false><<<pg, mvx::kPipeThreads, smem, st>>>(vp, grid);
+        }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         // tiles with more entries than the pipelined form takes (usually none): a small scanning grid
@@ -493,7 +508,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         vp.lent = (const float4*)(ws + pl.off_lent);
         vp.lbins = (const uint2*)(ws + pl.off_lbins);
         vp.tdesc = pl.form == FORM_PIPE ? (const mvx::TileDesc*)(ws + pl.off_tdesc) : nullptr;
-        vp.pipe_sc = pl.pipe_sc;
+        vp.pipe_sc = pl.pipe_sc; vp.pipe_q = pl.pipe_q;
         const unsigned long long nblk = (unsigned long long)B * pl.ncol * pl.nzc;
         if (nblk > 0x7fffffffULL) return fail(MVX_ERR_BAD_SHAPE, "batch too large for one launch; split it");
         const bool binary = spec->density_type == MVX_DENSITY_BINARY;

@@ -135,6 +135,7 @@ struct VoxParams {
     const uint2* lbins;
     const TileDesc* tdesc;     // pipelined form; for the tile form: non-null = only tiles with more than pipe_sc entries
     int pipe_sc;               // pipelined form: largest tile (entries) it takes; larger ones go to the tile form
+    int pipe_q;                // pipelined form: float4 words of the shared-memory entry ring
     void* out;                 // (B, Cout, D, D, D), element type by out_kind
     int out_kind;              // 0 fp32 (reference), 1 bf16, 2 fp16 (reduced-precision output)
 };
@@ -1573,7 +1574,11 @@ constexpr int kPipeSlots = 8;    // tiles in flight (descriptor + barrier slots)
 constexpr int kPipeSmemBytes = 232448;   // 227 KB: the whole SM
 constexpr int kPipeFixedBytes = kPipeSlots * ((int)sizeof(TileDesc) + 3 * 8 + 2 * 4) +
                                 kPipeWarps * kWarpList * ((int)sizeof(float4) + (int)sizeof(uint16_t));
-constexpr int kPipeRingQ = (kPipeSmemBytes - kPipeFixedBytes) / 16;   // float4 words of the entry ring
+// With several channel chunks per cell (C > 16) the weights of a cell's hits are computed once, cached per lane
+// (4 weights + the entry's shared address) and reused by the later chunks: kPipeHitCache hits per lane.
+constexpr int kPipeHitCache = 12;
+constexpr int kPipeCacheBytes = kPipeWarps * kPipeHitCache * 32 * ((int)sizeof(float4) + (int)sizeof(uint32_t));
+constexpr int pipe_ring_q(bool multi) { return (kPipeSmemBytes - kPipeFixedBytes - (multi ? kPipeCacheBytes : 0)) / 16; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -1636,17 +1641,20 @@ __device__ __forceinline__ uint32_t lds16(uint32_t a) {
 __device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory");
 }
 
-template <int MODE, int CH, bool BINARY, bool O16>
+template <int MODE, int CH, bool BINARY, bool O16, bool MULTI>
 __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(const VoxParams P, const unsigned ntiles) {
     constexpr int LPR = 4, RX = kCellX, RY = kCellY, CZ = kCellZ;
     constexpr int NCY = kTile / RY;
     constexpr int NW = kPipeWarps;
     constexpr int ND = kPipeSlots;
-    constexpr int Q = kPipeRingQ;
+    const int Q = P.pipe_q;   // float4 words of the entry ring (smaller when the hit cache is present)
 
     extern __shared__ __align__(128) float4 smem_q[];
     float4* const ring = smem_q;
@@ -1658,7 +1666,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
     int* const sNext = sOff + ND;                                      // slot s: next work item (cell x channel chunk) to hand out
     // warp lists: float4 words [WA0, WA0 + NW * kWarpList) of smem_q (record A of each listed atom), then their
     // entry indices (u16).  Hot code indexes smem_q directly so that every access is a plain shared-memory one.
-    constexpr int WA0 = Q + kPipeSlots * ((int)sizeof(TileDesc) + 3 * 8 + 2 * 4) / 16;
+    const int WA0 = Q + kPipeSlots * ((int)sizeof(TileDesc) + 3 * 8 + 2 * 4) / 16;
     uint32_t sq = smem_u32(smem_q);   // shared address of smem_q, pinned in a register
     asm volatile("" : "+r"(sq));
 
@@ -1766,6 +1774,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
             const uint32_t ebytes = (uint32_t)ES4 * 16u;
             const uint32_t wAq = sq + (uint32_t)(WA0 + warp * kWarpList) * 16u;                       // warp list: record A
             const uint32_t wIq = sq + (uint32_t)(WA0 + NW * kWarpList) * 16u + (uint32_t)(warp * kWarpList) * 2u;   // entry index
+            // hit cache (MULTI): lane-major float4 weights, then the entries' shared addresses
+            const uint32_t cw0 = sq + (uint32_t)(WA0 + NW * kWarpList) * 16u + (uint32_t)(NW * kWarpList) * 2u;
+            const uint32_t cwq = cw0 + (uint32_t)(warp * kPipeHitCache * 32) * 16u + (uint32_t)lane * 16u;
+            const uint32_t ceq = cw0 + (uint32_t)(NW * kPipeHitCache * 32) * 16u + (uint32_t)(warp * kPipeHitCache * 32) * 4u + (uint32_t)lane * 4u;
             // cells are handed out dynamically: the producer warp and warps that drew heavy cells simply take fewer
             for (;;) {
                 int cell = 0;
@@ -1787,6 +1799,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
                 int base = base0, wn = 0;
                 uint32_t mask_lo = 0u, mask_hi = 0u;
                 float acc[CH][4];
+                bool single = false;   // the whole layer fits one warp list
 
                 // 1. warp filter over this cell's layer: atoms whose mask names the cell, order kept;
                 // 2. every lane tests the warp list against the nearest of its 4 voxels -> hit bitmasks
@@ -1822,10 +1835,53 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
                             if (near_hit(lds128(wAq + (uint32_t)j * 16u))) mask_hi |= 1u << (j - 32);
                     }
                 };
+                // adds one hit (weights w of this lane's 4 voxels, entry at shared address eb) to the channel chunk at c0
+                auto accumulate = [&](const uint32_t eb, const float (&w)[4], const int c0, const uint32_t typew) {
+                    if (MODE == 0) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc[0][k] += w[k];
+                    } else if (MODE == 1) {
+                        const int ct = (int)typew - c0;
+#pragma unroll
+                        for (int c = 0; c < CH; ++c)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) acc[c][k] += (ct == c) ? w[k] : 0.f;
+                    } else if (CH >= 4) {
+                        const uint32_t fb = eb + 48u + (uint32_t)c0 * 4u;
+#pragma unroll
+                        for (int c4 = 0; c4 < CH; c4 += 4) {
+                            const float4 fv = lds128(fb + (uint32_t)c4 * 4u);
+                            const float f[4] = {fv.x, fv.y, fv.z, fv.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {   // channel pairs through the packed FMA
+                                ffma2(acc[c4][k], acc[c4 + 1][k], f[0], f[1], w[k]);
+                                ffma2(acc[c4 + 2][k], acc[c4 + 3][k], f[2], f[3], w[k]);
+                            }
+                        }
+                    } else {
+                        const float f = __uint_as_float(lds32(eb + 48u + (uint32_t)c0 * 4u));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc[0][k] = fmaf(f, w[k], acc[0][k]);
+                    }
+                };
                 // 3. lane-private walk over the set bits, ascending (fixed fp32 summation order); the trip count
-                //    is the largest hit count of the warp
+                //    is the largest hit count of the warp.  MULTI: chunk 0 caches each hit's weights, later chunks replay them.
                 auto walk = [&](uint32_t mlo, uint32_t mhi, const int c0) {
-                    const int nmax = (int)__reduce_max_sync(0xffffffffu, (unsigned)(__popc(mlo) + __popc(mhi)));
+                    const int mycnt = __popc(mlo) + __popc(mhi);
+                    const int nmax = (int)__reduce_max_sync(0xffffffffu, (unsigned)mycnt);
+                    const bool cached = MULTI && single && nmax <= kPipeHitCache;   // warp-uniform
+                    if (MULTI && cached && c0 != P.c_begin) {
+                        for (int h = 0; h < nmax; ++h) {
+                            if (h < mycnt) {
+                                const float4 wv = lds128(cwq + (uint32_t)h * 512u);
+                                const uint32_t eb = lds32(ceq + (uint32_t)h * 128u);
+                                const float w[4] = {wv.x, wv.y, wv.z, wv.w};
+                                accumulate(eb, w, c0, MODE == 1 ? lds32(eb + 28u) : 0u);
+                            }
+                        }
+                        __syncwarp();
+                        return;
+                    }
                     for (int h = 0; h < nmax; ++h) {
                         if ((mlo | mhi) != 0u) {
                             int j;
@@ -1870,32 +1926,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) w[k] = off[k] ? 0.f : w[k];
                             }
-                            if (MODE == 0) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) acc[0][k] += w[k];
-                            } else if (MODE == 1) {
-                                const int ct = __float_as_int(Bv.w) - c0;
-#pragma unroll
-                                for (int c = 0; c < CH; ++c)
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) acc[c][k] += (ct == c) ? w[k] : 0.f;
-                            } else if (CH >= 4) {
-                                const uint32_t fb = eb + 48u + (uint32_t)c0 * 4u;
-#pragma unroll
-                                for (int c4 = 0; c4 < CH; c4 += 4) {
-                                    const float4 fv = lds128(fb + (uint32_t)c4 * 4u);
-                                    const float f[4] = {fv.x, fv.y, fv.z, fv.w};
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) {   // channel pairs through the packed FMA
-                                        ffma2(acc[c4][k], acc[c4 + 1][k], f[0], f[1], w[k]);
-                                        ffma2(acc[c4 + 2][k], acc[c4 + 3][k], f[2], f[3], w[k]);
-                                    }
-                                }
-                            } else {
-                                const float f = __uint_as_float(lds32(eb + 48u + (uint32_t)c0 * 4u));
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) acc[0][k] = fmaf(f, w[k], acc[0][k]);
+                            if (MULTI && cached) {
+                                sts128(cwq + (uint32_t)h * 512u, make_float4(w[0], w[1], w[2], w[3]));
+                                sts32(ceq + (uint32_t)h * 128u, eb);
                             }
+                            accumulate(eb, w, c0, __float_as_uint(Bv.w));
                         }
                     }
                     __syncwarp();
@@ -1924,7 +1959,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
                 // When the whole layer fits one warp list (the common case) its hit masks serve every channel chunk;
                 // otherwise each chunk walks the layer's list rounds again.
                 build_list();
-                const bool single = base >= end;
+                single = base >= end;
                 for (int c0 = P.c_begin; c0 < P.c_end; c0 += CH) {
                     clear();
                     if (!single && c0 != P.c_begin) { base = base0; build_list(); }
