@@ -37,7 +37,7 @@ enum { MVX_DENSITY_GAUSSIAN = 0, MVX_DENSITY_BINARY = 1 };          /* base/voxe
 enum { MVX_RADII_SCALAR = 0, MVX_RADII_CHANNEL_WISE = 1, MVX_RADII_ATOM_WISE = 2 }; /* base/voxelizer.py:12 */
 enum { MVX_MODE_SINGLE = 0, MVX_MODE_TYPES = 1, MVX_MODE_FEATURES = 2 };            /* base/voxelizer.py:121-128 */
 enum { MVX_F32 = 0, MVX_F64 = 1 };
-enum { MVX_OUT_F32 = 0, MVX_OUT_BF16 = 1, MVX_OUT_F16 = 2 };   /* element type of the output grid */
+enum { MVX_OUT_F32 = 0, MVX_OUT_BF16 = 1, MVX_OUT_F16 = 2, MVX_OUT_F64 = 3 };   /* element type of the output grid */
 
 /* Constructor arguments of the reference Voxelizer (base/voxelizer.py:15-38, numpy/voxelizer.py:22-35). */
 typedef struct mvx_grid_spec {
@@ -87,7 +87,9 @@ typedef struct mvx_batch {
                                        numpy/transform.py:43-80), fused into the per-atom prep kernel. */
     int32_t        out_dtype;       /* MVX_OUT_F32 (the reference's precision=32 layout, default) or a
                                        reduced-precision grid: every voxel is computed in fp32 exactly as
-                                       for MVX_OUT_F32 and rounded once (nearest-even) on the store. */
+                                       for MVX_OUT_F32 and rounded once (nearest-even) on the store.
+                                       MVX_OUT_F64 is the reference's precision=64 (numpy/voxelizer.py:28-34):
+                                       distances, kernel and accumulation in fp64, float64 grid (untuned path). */
 } mvx_batch;
 
 /* Bytes of device workspace mvx_voxelize needs for this spec/batch (256-byte aligned base). */

@@ -29,7 +29,7 @@ DENSITY = {"gaussian": 0, "binary": 1}
 RADII = {"scalar": 0, "channel-wise": 1, "atom-wise": 2}
 MODE = {"single": 0, "types": 1, "features": 2}
 FORM_KERNEL = {0: "mvx_voxelize_kernel", 1: "mvx_voxelize_cells_kernel", 3: "mvx_voxelize_tiles_kernel", 4: "mvx_voxelize_pipe_kernel"}
-OUT_DTYPE = {"float32": 0, "bfloat16": 1, "float16": 2}
+OUT_DTYPE = {"float32": 0, "bfloat16": 1, "float16": 2, "float64": 3}
 
 
 class GridSpec(ctypes.Structure):

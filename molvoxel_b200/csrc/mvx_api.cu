@@ -77,7 +77,7 @@ int check_args(const mvx_grid_spec* s, const mvx_batch* b) {
     if (b->out_channels < C)   // numpy/voxelizer.py:337 (types), :192 (features), :450 (single)
         return fail(MVX_ERR_BAD_SHAPE, "Output channel is less than number of types");
     if (b->mode != MVX_MODE_TYPES && b->out_channels != C) return fail(MVX_ERR_BAD_SHAPE, "Output grid dimension incorrect");
-    if (b->out_dtype < MVX_OUT_F32 || b->out_dtype > MVX_OUT_F16) return fail(MVX_ERR_BAD_ENUM, "out_dtype");
+    if (b->out_dtype < MVX_OUT_F32 || b->out_dtype > MVX_OUT_F64) return fail(MVX_ERR_BAD_ENUM, "out_dtype");
     if (b->num_mols > 0 && !b->mol_offsets) return fail(MVX_ERR_NULL_POINTER, "mol_offsets");
     if (b->total_atoms > 0) {
         if (!b->coords) return fail(MVX_ERR_NULL_POINTER, "coords");
@@ -144,6 +144,10 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
         g.r_scalar32 = rmax;
         g.clip_lo = (double)((float)g.lower - rmax);
         g.clip_hi = (double)((float)g.upper + rmax);
+        if (b->out_dtype == MVX_OUT_F64) {   // precision=64: radii.astype(float64).max() keeps the bounds in fp64
+            g.clip_lo = g.lower - (double)rmax;
+            g.clip_hi = g.upper + (double)rmax;
+        }
         reach = (double)rmax;
     } else {
         g.radii_src = (s->radii_type == MVX_RADII_ATOM_WISE) ? 1 : 2;
@@ -195,6 +199,7 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
             else if (pl->nv == 4 && std::strcmp(e, "tiles") == 0) pl->form = FORM_TILES;
             else if (pl->nv == 4 && std::strcmp(e, "pipe") == 0) pl->form = FORM_PIPE;
         }
+        if (b->out_dtype == MVX_OUT_F64) pl->form = FORM_ROWS;   // precision=64 runs on the generic column lists
         // channel-wise features patch the staged radii per channel pass, which needs the CTA-synchronous staging
         if (pl->form == FORM_PIPE && chan_feat) pl->form = per_col >= 200.0 ? FORM_TILES : FORM_CELLS;
     }
@@ -381,7 +386,7 @@ int mvx_launches_per_call(const mvx_grid_spec* spec, const mvx_batch* batch) {
     if (rc != MVX_OK) return rc;
     if (batch->num_mols == 0) return 0;
     const bool chan_feat = batch->mode == MVX_MODE_FEATURES && spec->radii_type == MVX_RADII_CHANNEL_WISE;
-    int nvox = chan_feat ? batch->num_channels : 1;
+    int nvox = (chan_feat && batch->out_dtype != MVX_OUT_F64) ? batch->num_channels : 1;
     const int nbin = layered(pl.form) ? (batch->total_atoms > 0 ? 3 : 1) : (bin_groups(batch->num_mols, pl.ncol) <= 1 ? 1 : 2);   // scan, place, build
     const int nexp = (pl.form == FORM_CELLS && batch->total_atoms > 0) ? 1 : 0;
     return (batch->total_atoms > 0 ? 1 : 0) + nbin + nexp + nvox * (pl.form == FORM_PIPE ? 2 : 1);   // prep + bin + expand + voxelize
@@ -513,7 +518,20 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         if (nblk > 0x7fffffffULL) return fail(MVX_ERR_BAD_SHAPE, "batch too large for one launch; split it");
         const bool binary = spec->density_type == MVX_DENSITY_BINARY;
         const bool chan_feat = batch->mode == MVX_MODE_FEATURES && spec->radii_type == MVX_RADII_CHANNEL_WISE;
-        if (chan_feat) {   // per-channel radius: one pass per channel (numpy/voxelizer.py:213-224)
+        if (batch->out_dtype == MVX_OUT_F64) {   // precision=64 (untuned): fp64 arithmetic and output
+            mvx::VoxF64Params fp;
+            fp.res = pl.geo.res; fp.half_width = pl.geo.half_width; fp.sigma = spec->sigma; fp.radius = batch->radius;
+            fp.dim = spec->dimension; fp.ncx = pl.geo.ncx; fp.ncol = pl.ncol; fp.mode = batch->mode; fp.C = C;
+            fp.Cout = batch->out_channels; fp.maxcols = pl.maxcols; fp.binary = binary;
+            fp.scalar_radius = spec->radii_type == MVX_RADII_SCALAR;
+            fp.mol_offsets = batch->mol_offsets; fp.recs = recs; fp.bins = bins; fp.lists = lists;
+            fp.types = batch->types; fp.features = batch->features; fp.chan_radii = chan_feat ? batch->radii : nullptr;
+            fp.out = (double*)out;
+            const unsigned long long nb64 = (unsigned long long)B * pl.ncol;
+            if (nb64 > 0x7fffffffULL) return fail(MVX_ERR_BAD_SHAPE, "batch too large for one launch; split it");
+            mvx::mvx_voxelize_f64_kernel<<<(unsigned)nb64, 256, 0, st>>>(fp);
+            MVX_CUDA_OK(cudaGetLastError());
+        } else if (chan_feat) {   // per-channel radius: one pass per channel (numpy/voxelizer.py:213-224)
             for (int c = 0; c < C; ++c) {
                 vp.c_begin = c; vp.c_end = c + 1; vp.chan_radii = batch->radii;
                 MVX_CUDA_OK(launch_vox(batch->mode, 1, vp, binary, pl.form, pl.nv, (unsigned)nblk, st));

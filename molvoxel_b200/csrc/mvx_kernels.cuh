@@ -1571,7 +1571,10 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_sweep_kernel(const V
 constexpr int kPipeThreads = MVX_PIPE_THREADS;   // 12 warps: 168 registers per thread, no spills
 constexpr int kPipeWarps = kPipeThreads / 32;
 constexpr int kPipeSlots = 8;    // tiles in flight (descriptor + barrier slots)
-constexpr int kPipeSmemBytes = 232448;   // 227 KB: the whole SM
+#ifndef MVX_PIPE_SMEM
+#define MVX_PIPE_SMEM 232448
+#endif
+constexpr int kPipeSmemBytes = MVX_PIPE_SMEM;   // 227 KB: the whole SM
 constexpr int kPipeFixedBytes = kPipeSlots * ((int)sizeof(TileDesc) + 3 * 8 + 2 * 4) +
                                 kPipeWarps * kWarpList * ((int)sizeof(float4) + (int)sizeof(uint16_t));
 // With several channel chunks per cell (C > 16) the weights of a cell's hits are computed once, cached per lane
@@ -1984,6 +1987,88 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// voxelize, precision = 64 (the reference's `precision=64` constructor argument, numpy/voxelizer.py:28-34; SURVEY
+// row f4): distances, dr = dist / r, the Gaussian and the accumulation all in fp64, (B, Cout, D, D, D) float64 out.
+// API completeness, not a tuned path: one CTA per (molecule, 8x8 column) on the column lists of the generic form,
+// one thread per voxel, atoms in ascending order.
+// ---------------------------------------------------------------------------------------------
+struct VoxF64Params {
+    double res, half_width, sigma, radius;
+    int dim, ncx, ncol, mode, C, Cout, maxcols, binary;
+    int scalar_radius;          // 1: every atom uses `radius` (python float); 0: the atom record's fp32 radius, widened
+    const int32_t* mol_offsets;
+    const AtomRec* recs;
+    const uint2* bins;
+    const uint32_t* lists;
+    const int32_t* types;
+    const float* features;
+    const float* chan_radii;    // features + channel-wise radii: (C,) fp32, else nullptr
+    double* out;
+};
+
+__device__ __forceinline__ double term_f64(double s, double r, double sigma, int binary) {
+    const double dr = __ddiv_rn(__dsqrt_rn(s), r);
+    if (dr > 1.0) return 0.0;
+    if (binary) return 1.0;
+    const double q = __ddiv_rn(dr, sigma);
+    return exp(-0.5 * __dmul_rn(q, q));
+}
+
+__global__ void __launch_bounds__(256) mvx_voxelize_f64_kernel(const VoxF64Params P) {
+    const int col = blockIdx.x % P.ncol, mol = blockIdx.x / P.ncol;
+    const int x0 = (col / P.ncx) * kTile, y0 = (col % P.ncx) * kTile;
+    const int D = P.dim;
+    const size_t plane = (size_t)D * D * D;
+    const uint2 bin = P.bins[(size_t)mol * P.ncol + col];
+    const int cnt = (int)bin.y;
+    const uint32_t* list = P.lists + (size_t)P.mol_offsets[mol] * (size_t)P.maxcols + bin.x;
+    double* out_mol = P.out + (size_t)mol * P.Cout * plane;
+    for (int item = threadIdx.x; item < kTile * kTile * D; item += blockDim.x) {
+        const int row = item / D, z = item - row * D;
+        const int x = x0 + (row >> 3), y = y0 + (row & 7);
+        if (x >= D || y >= D) continue;
+        const double gx = __dsub_rn(__dmul_rn((double)x, P.res), P.half_width);
+        const double gy = __dsub_rn(__dmul_rn((double)y, P.res), P.half_width);
+        const double gz = __dsub_rn(__dmul_rn((double)z, P.res), P.half_width);
+        const size_t vox = ((size_t)x * D + y) * D + z;
+        for (int c0 = 0; c0 < P.Cout; c0 += 4) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int j = 0; j < cnt; ++j) {
+                const uint32_t n = list[j];
+                const AtomRec rec = P.recs[n];
+                if (rec.fx == x || rec.fy == y || rec.fz == z) continue;   // the reference's block cull (forbidden planes)
+                const double dx = __dsub_rn(rec.px, gx), dy = __dsub_rn(rec.py, gy), dz = __dsub_rn(rec.pz, gz);
+                const double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                if (P.chan_radii != nullptr) {   // features, channel-wise radii: the kernel radius is the channel's
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c0 + c < P.C)
+                            acc[c] += (double)P.features[(size_t)n * P.C + c0 + c] * term_f64(s, (double)P.chan_radii[c0 + c], P.sigma, P.binary);
+                    continue;
+                }
+                const double r = P.scalar_radius ? P.radius : (double)rec.r;
+                if (s > r * r * 1.000001) continue;   // clearly outside (dr > 1): contributes exactly 0
+                const double t = term_f64(s, r, P.sigma, P.binary);
+                if (P.mode == 0) {
+                    if (c0 == 0) acc[0] += t;
+                } else if (P.mode == 1) {
+                    const int ch = P.types[n] - c0;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[c] += (ch == c) ? t : 0.0;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c0 + c < P.C) acc[c] += (double)P.features[(size_t)n * P.C + c0 + c] * t;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c0 + c < P.Cout) out_mol[(size_t)(c0 + c) * plane + vox] = acc[c];
+        }
     }
 }
 

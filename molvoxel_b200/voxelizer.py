@@ -68,7 +68,13 @@ class Voxelizer:
             self.device = torch.device("cuda", torch.cuda.current_device())
         # fp32 is the reference (precision=32).  bfloat16 / float16 grids are computed in fp32 exactly like the
         # fp32 grid and rounded once on the store: half the bytes of the write-bound op.
-        assert out_dtype in (torch.float32, torch.bfloat16, torch.float16), "out_dtype must be float32, bfloat16 or float16"
+        # precision=64 (reference numpy/voxelizer.py:28-34) = a float64 grid computed in fp64 (untuned).
+        precision = kwargs.get("precision", 32)
+        assert precision in [32, 64]
+        if precision == 64:
+            out_dtype = torch.float64
+        assert out_dtype in (torch.float32, torch.bfloat16, torch.float16, torch.float64), \
+            "out_dtype must be float32, bfloat16, float16 or float64"
         self.out_dtype = out_dtype
         self._ws = None
         self._pipe = None

@@ -61,6 +61,21 @@ static inline float pair_term(double px, double py, double pz, double gx, double
     return e;
 }
 
+/* The same term with precision=64 (numpy/voxelizer.py:34): dist stays fp64 (:545 is a no-op), dr = dist / radii in fp64
+ * (:548), np.exp(-0.5 * (dr / sigma) ** 2) in fp64 (:558), cutoff dr > 1.0 (:559) / dr <= 1.0 (:555). */
+static inline double pair_term64(double px, double py, double pz, double gx, double gy, double gz,
+                                 double r, double sigma, int binary) {
+    double dx = px - gx, dy = py - gy, dz = pz - gz;
+    double xx = dx * dx, yy = dy * dy, zz = dz * dz;
+    double s = (xx + yy) + zz;
+    double dr = sqrt(s) / r;
+    if (binary) return (dr <= 1.0) ? 1.0 : 0.0;
+    double q = dr / sigma;
+    double e = exp(-0.5 * (q * q));
+    if (dr > 1.0) e = 0.0;
+    return e;
+}
+
 /*
  * One molecule.  coords: (V,3) f32|f64; center: (3,) f32|f64 or NULL; types: (V,) int32
  * (values already reduced to int16 range by the caller); features: (V,C) f32;
@@ -69,9 +84,11 @@ static inline float pair_term(double px, double py, double pz, double gx, double
  *
  * Follows forward_types :240-315, forward_features :97-169, forward_single :370-436.
  */
-int mvxo_forward(const mvxo_spec *s, int mode, int V, const void *coords, int coords_f64,
-                 const void *center, int center_f64, const int32_t *types, const float *features,
-                 int C, double radius, const float *radii, float *out, int out_channels) {
+static int mvxo_forward_p(const mvxo_spec *s, int mode, int V, const void *coords, int coords_f64,
+                          const void *center, int center_f64, const int32_t *types, const float *features,
+                          int C, double radius, const float *radii, void *out_v, int out_channels, int prec64) {
+    float *out = (float *)out_v;      /* precision=32 (the default oracle) */
+    double *out64 = (double *)out_v;  /* precision=64: get_empty_grid dtype :60-70, features/radii astype(fp64) :127-130 */
     const int D = s->dimension;
     const int bd = s->blockdim > 0 ? s->blockdim : 8;
     const int nb = (D + bd - 1) / bd;                     /* :44 */
@@ -87,7 +104,7 @@ int mvxo_forward(const mvxo_spec *s, int mode, int V, const void *coords, int co
     if (mode != MVXO_MODE_SINGLE && C > out_channels) return -2;                    /* :337 */
 
     /* out init: types/single zero (:279-281, :402-404); features writes every voxel (:158-160,:232-235). */
-    memset(out, 0, sizeof(float) * plane * (size_t)out_channels);
+    memset(out_v, 0, (prec64 ? sizeof(double) : sizeof(float)) * plane * (size_t)out_channels);
     if (V == 0) return 0;
 
     double *p = (double *)malloc(sizeof(double) * 3 * (size_t)V);
@@ -125,7 +142,7 @@ int mvxo_forward(const mvxo_spec *s, int mode, int V, const void *coords, int co
         float m = radii[0];
         for (int c = 1; c < C; ++c) if (radii[c] > m) m = radii[c];
         size_scalar = (double)m;
-        thr_f32 = 1;
+        thr_f32 = !prec64;   /* precision=64: radii.astype(float64).max() is np.float64, the bounds stay fp64 (:130, :138) */
     }
     for (int n = 0; n < V; ++n) {
         if (s->radii_mode == MVXO_RADII_SCALAR) rr[n] = (float)radius;
@@ -211,6 +228,21 @@ int mvxo_forward(const mvxo_spec *s, int mode, int V, const void *coords, int co
                     for (int z = az0; z < az1; ++z) {
                         double gz = axis_at(s, z, half_width);
                         size_t vox = ((size_t)x * D + y) * D + z;
+                        if (prec64) {   /* the same accumulation in fp64 (array radii are fp32 at the C boundary, widened) */
+                            if (mode == MVXO_MODE_FEATURES && s->radii_mode == MVXO_RADII_CHANNEL) {
+                                for (int c = 0; c < C; ++c)
+                                    out64[(size_t)c * plane + vox] += (double)features[(size_t)n * C + c] *
+                                        pair_term64(px, py, pz, gx, gy, gz, (double)radii[c], s->sigma, s->binary);
+                            } else {
+                                double r64 = (s->radii_mode == MVXO_RADII_SCALAR) ? radius : (double)rr[n];
+                                double t = pair_term64(px, py, pz, gx, gy, gz, r64, s->sigma, s->binary);
+                                if (mode == MVXO_MODE_TYPES) out64[(size_t)types[n] * plane + vox] += t;
+                                else if (mode == MVXO_MODE_SINGLE) out64[vox] += t;
+                                else if (t != 0.0)
+                                    for (int c = 0; c < C; ++c) out64[(size_t)c * plane + vox] += (double)features[(size_t)n * C + c] * t;
+                            }
+                            continue;
+                        }
                         if (mode == MVXO_MODE_TYPES) {
                             float t = pair_term(px, py, pz, gx, gy, gz, rr[n], sigma32, s->binary);
                             out[(size_t)types[n] * plane + vox] += t;            /* :365 */
@@ -241,6 +273,21 @@ int mvxo_forward(const mvxo_spec *s, int mode, int V, const void *coords, int co
     }
     free(p); free(rr); free(keep); free(blist); free(bounds);
     return 0;
+}
+
+int mvxo_forward(const mvxo_spec *s, int mode, int V, const void *coords, int coords_f64,
+                 const void *center, int center_f64, const int32_t *types, const float *features,
+                 int C, double radius, const float *radii, float *out, int out_channels) {
+    return mvxo_forward_p(s, mode, V, coords, coords_f64, center, center_f64, types, features, C, radius, radii, out,
+                          out_channels, 0);
+}
+
+/* precision=64 variant: out is (out_channels, D, D, D) float64. */
+int mvxo_forward64(const mvxo_spec *s, int mode, int V, const void *coords, int coords_f64,
+                   const void *center, int center_f64, const int32_t *types, const float *features,
+                   int C, double radius, const float *radii, double *out, int out_channels) {
+    return mvxo_forward_p(s, mode, V, coords, coords_f64, center, center_f64, types, features, C, radius, radii, out,
+                          out_channels, 1);
 }
 
 /*

@@ -43,6 +43,7 @@ def _load():
         _lib = ctypes.CDLL(_SO)
         _lib.mvxo_forward_batch.restype = ctypes.c_int
         _lib.mvxo_forward.restype = ctypes.c_int
+        _lib.mvxo_forward64.restype = ctypes.c_int
     return _lib
 
 
@@ -56,8 +57,9 @@ def _ptr(a):
 
 def oracle_forward_batch(resolution, dimension, radii_type, density_type, sigma, blockdim, mode,
                          mol_offsets, coords, centers, types, features, num_channels, radii,
-                         out_channels=None, num_threads=1):
-    """B independent reference calls over a CSR batch; returns (B, C, D, D, D) float32."""
+                         out_channels=None, num_threads=1, precision=32):
+    """B independent reference calls over a CSR batch; returns (B, C, D, D, D) float32 (float64 with precision=64,
+    the reference's `precision` constructor argument, numpy/voxelizer.py:28-34)."""
     lib = _load()
     spec = _Spec(float(resolution), int(dimension), int(density_type == "binary"), float(sigma),
                  _RADII[radii_type], int(blockdim) if blockdim else 8)
@@ -82,6 +84,23 @@ def oracle_forward_batch(resolution, dimension, radii_type, density_type, sigma,
         radii_arr = np.ascontiguousarray(radii, dtype=np.float32)
     C = int(num_channels)
     oc = int(out_channels) if out_channels is not None else C
+    if precision == 64:   # molecule by molecule through mvxo_forward64
+        out = np.empty((B, oc, dimension, dimension, dimension), dtype=np.float64)
+        csz, zsz = coords.dtype.itemsize * 3, (centers.dtype.itemsize * 3 if centers is not None else 0)
+        for m in range(B):
+            a, b = int(mol_offsets[m]), int(mol_offsets[m + 1])
+            cen = None if centers is None else ctypes.c_void_p(centers.ctypes.data + zsz * m)
+            rad = radii_arr
+            if radii_arr is not None and radii_type == "atom-wise":
+                rad = radii_arr[a:b]
+            rc = lib.mvxo_forward64(
+                ctypes.byref(spec), _MODE[mode], b - a, ctypes.c_void_p(coords.ctypes.data + csz * a),
+                int(coords.dtype == np.float64), cen, int(centers is not None and centers.dtype == np.float64),
+                None if types is None else _ptr(types[a:b]), None if features is None else _ptr(features[a:b]),
+                C, ctypes.c_double(radius), _ptr(rad), _ptr(out[m]), oc)
+            if rc != 0:
+                raise AssertionError(f"oracle rejected the arguments (code {rc})")
+        return out
     out = np.empty((B, oc, dimension, dimension, dimension), dtype=np.float32)
     rc = lib.mvxo_forward_batch(
         ctypes.byref(spec), _MODE[mode], B, _ptr(mol_offsets), _ptr(coords), int(coords.dtype == np.float64),

@@ -572,3 +572,53 @@ def test_size_independent_properties_full_dense_batch():
         assert torch.equal(vox.forward_features(coords[a:b], None, feats[a:b], 1.0), out[m])
     mass = out.sum(dim=(1, 2, 3, 4)).cpu().numpy()
     assert (mass > 0.5 * V).all() and np.isfinite(mass).all()
+
+
+def _p64_names():
+    import glob
+    import os
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "p64")
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(d, "*.npz")))
+
+
+@pytest.mark.parametrize("name", _p64_names())
+def test_precision64_matches_reference_golden(name):
+    """create_voxelizer(..., precision=64) against fixtures of the live reference's precision=64
+    numpy backend: binary types/single bit-exact, the rest identical support and <= 1e-12 of the peak."""
+    from tests.test_oracle_golden import load_p64
+    g = load_p64(name)
+    cfg = g["cfg"]
+    vox = mv.create_voxelizer(cfg["resolution"], cfg["dimension"], cfg["radii_type"], cfg["density_type"], library="b200",
+                              blockdim=cfg.get("blockdim"), precision=64)
+    if cfg["mode"] == "types":
+        out = vox.forward_types(g["coords"], g["center"], g["channels"], g["radii"])
+    elif cfg["mode"] == "features":
+        out = vox.forward_features(g["coords"], g["center"], g["channels"], g["radii"])
+    else:
+        out = vox.forward_single(g["coords"], g["center"], g["radii"])
+    assert out.dtype == torch.float64
+    got, ref = out.cpu().numpy(), g["ref"]
+    assert got.shape == ref.shape
+    if cfg["density_type"] == "binary" and cfg["mode"] != "features":
+        assert np.array_equal(got, ref)
+    else:
+        assert np.array_equal(got != 0, ref != 0)
+        assert float(np.abs(got - ref).max()) <= 1e-12 * max(1.0, float(np.abs(ref).max()))
+
+
+def test_precision64_batch_vs_oracle_and_fp32():
+    """A ragged ligand batch in fp64 against the fp64 oracle; the fp32 grid is its rounding up to 1e-6."""
+    rng = np.random.default_rng(64)
+    offs, coords, types = ligand_batch(rng, 7, 5, 10, 40)
+    centers = rng.normal(scale=0.4, size=(7, 3))
+    v64 = mv.create_voxelizer(0.5, 32, "scalar", "gaussian", library="b200", precision=64)
+    v32 = mv.create_voxelizer(0.5, 32, "scalar", "gaussian", library="b200")
+    a = v64.forward_types_batch(coords, offs, centers, types, 1.0, 6)       # one surplus channel stays zero
+    ref = oracle_forward_batch(0.5, 32, "scalar", "gaussian", 0.5, 8, "types", offs, coords, centers, types, None, 5, 1.0,
+                               out_channels=6, precision=64)
+    got = a.cpu().numpy()
+    assert np.array_equal(got != 0, ref != 0) and float(np.abs(got - ref).max()) <= 1e-12 * float(ref.max())
+    assert float(got[:, 5].max()) == 0.0
+    b = v32.forward_types_batch(coords, offs, centers, types, 1.0, 6)
+    assert float((a.float() - b).abs().max()) <= 2e-6 * float(ref.max())
+    assert v64.get_empty_grid(3).dtype == torch.float64
