@@ -622,3 +622,18 @@ def test_precision64_batch_vs_oracle_and_fp32():
     b = v32.forward_types_batch(coords, offs, centers, types, 1.0, 6)
     assert float((a.float() - b).abs().max()) <= 2e-6 * float(ref.max())
     assert v64.get_empty_grid(3).dtype == torch.float64
+
+
+def test_pipelined_form_large_grid_many_layers():
+    """160^3 at resolution 0.25: three z chunks of 56 voxels (layers 16,16,16,8), 12 global layers, 400 columns;
+    dense enough for the pipelined form by default.  Binary single-channel, bit-exact against the oracle."""
+    rng = np.random.default_rng(160)
+    dim, res, V = 160, 0.25, 30000
+    half = res * (dim - 1) / 2
+    coords = rng.uniform(-half - 0.5, half + 0.5, size=(V, 3))
+    radii = rng.uniform(0.6, 1.0, size=V).astype(np.float32)
+    vox = mv.create_voxelizer(res, dim, "atom-wise", "binary", library="b200")
+    out = vox.forward_single(coords, np.zeros(3), radii)
+    vox.check_status()
+    ref = OracleVoxelizer(res, dim, "atom-wise", "binary").forward_single(coords, np.zeros(3), radii)
+    assert np.array_equal(out.cpu().numpy(), ref)
