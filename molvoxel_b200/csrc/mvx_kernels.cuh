@@ -669,13 +669,26 @@ __global__ void __launch_bounds__(256) mvx_lbuild_kernel(const LBinParams P) {
             const int i = i0 + lane, nv = min(32, S - i0);
             if (i < S) {
                 const uint32_t n = srt[i];
+                float4* e = stage + lane * ES4;
+                // the first four feature words are requested before the record arithmetic (independent loads in
+                // flight together); wider rows follow in groups of four
+                const float* f = P.features + (size_t)n * P.C;
+                const int nf = P.mode == 2 ? ES4 - 3 : 0;
+                float4 fw[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) fw[k] = k < nf ? feature_word(f, k) : make_float4(0.f, 0.f, 0.f, 0.f);
                 float4 e0, e1, e2;
                 make_entry(n, e0, e1, e2);
-                float4* e = stage + lane * ES4;
                 e[0] = e0; e[1] = e1; e[2] = e2;
-                if (P.mode == 2) {
-                    const float* f = P.features + (size_t)n * P.C;
-                    for (int k = 0; k < ES4 - 3; ++k) e[3 + k] = feature_word(f, k);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < nf) e[3 + k] = fw[k];
+                for (int k0 = 4; k0 < nf; k0 += 4) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) fw[k] = k0 + k < nf ? feature_word(f, k0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k0 + k < nf) e[3 + k0 + k] = fw[k];
                 }
             }
             __syncwarp();
