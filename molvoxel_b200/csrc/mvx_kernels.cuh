@@ -1869,9 +1869,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
                             const float4 fv = lds128(fb + (uint32_t)c4 * 4u);
                             const float f[4] = {fv.x, fv.y, fv.z, fv.w};
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {   // channel pairs through the packed FMA
-                                ffma2(acc[c4][k], acc[c4 + 1][k], f[0], f[1], w[k]);
-                                ffma2(acc[c4 + 2][k], acc[c4 + 3][k], f[2], f[3], w[k]);
+                            for (int c = 0; c < 4; ++c) {   // packed FMA over voxel pairs: the accumulators of a channel stay one
+                                ffma2(acc[c4 + c][0], acc[c4 + c][1], w[0], w[1], f[c]);   // float4 in register order, so the
+                                ffma2(acc[c4 + c][2], acc[c4 + c][3], w[2], w[3], f[c]);   // stores need no shuffles
                             }
                         }
                     } else {
