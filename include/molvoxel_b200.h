@@ -36,7 +36,7 @@ typedef enum mvx_status {
 enum { MVX_DENSITY_GAUSSIAN = 0, MVX_DENSITY_BINARY = 1 };          /* base/voxelizer.py:13 */
 enum { MVX_RADII_SCALAR = 0, MVX_RADII_CHANNEL_WISE = 1, MVX_RADII_ATOM_WISE = 2 }; /* base/voxelizer.py:12 */
 enum { MVX_MODE_SINGLE = 0, MVX_MODE_TYPES = 1, MVX_MODE_FEATURES = 2 };            /* base/voxelizer.py:121-128 */
-enum { MVX_F32 = 0, MVX_F64 = 1 };
+enum { MVX_F32 = 0, MVX_F64 = 1, MVX_U8 = 2, MVX_F16 = 3 };   /* U8 / F16: compact feature rows only */
 enum { MVX_OUT_F32 = 0, MVX_OUT_BF16 = 1, MVX_OUT_F16 = 2, MVX_OUT_F64 = 3 };   /* element type of the output grid */
 
 /* Constructor arguments of the reference Voxelizer (base/voxelizer.py:15-38, numpy/voxelizer.py:22-35). */
@@ -57,7 +57,7 @@ typedef struct mvx_grid_spec {
  *   coords   (N,3)  f32|f64  atom coordinates                  (numpy/voxelizer.py:251)
  *   centers  (B,3)  f32|f64  or NULL = no centring             (:263)
  *   types    (N,)   int32    channel index per atom, TYPES     (:253)
- *   features (N,C)  f32      feature rows, FEATURES            (:110)
+ *   features (N,C)  f32      feature rows, FEATURES            (:110); u8 | f16 rows with features_dtype
  *   radius   python-float scalar when radii_type is SCALAR
  *   radii    (C,) f32 channel-wise | (N,) f32 atom-wise        (:111)
  *   transforms (B,12) f64 optional rigid transform per molecule (:265)
@@ -72,7 +72,7 @@ typedef struct mvx_batch {
     const void    *centers;
     int32_t        centers_dtype;
     const int32_t *types;
-    const float   *features;
+    const void    *features;        /* element type by features_dtype (f32 unless stated) */
     int32_t        num_channels;    /* C: channels the inputs address (types < C; features row length) */
     int32_t        out_channels;    /* channels of `out` (>= C; surplus channels are zero, :337) */
     double         radius;
@@ -90,6 +90,10 @@ typedef struct mvx_batch {
                                        for MVX_OUT_F32 and rounded once (nearest-even) on the store.
                                        MVX_OUT_F64 is the reference's precision=64 (numpy/voxelizer.py:28-34):
                                        distances, kernel and accumulation in fp64, float64 grid (untuned path). */
+    int32_t        features_dtype;  /* MVX_F32 (default) | MVX_U8 | MVX_F16: element type of `features`.  Compact rows
+                                       (one-hot / flag / count features) are widened to fp32 on the device, exactly —
+                                       the reference's features.astype(float32) (numpy/voxelizer.py:127-128) — so a
+                                       host caller moves 1/4 or 1/2 of the bytes over PCIe. */
 } mvx_batch;
 
 /* Bytes of device workspace mvx_voxelize needs for this spec/batch (256-byte aligned base). */

@@ -24,7 +24,7 @@ NVCC_FLAGS = [
 MVX_OK = 0
 MVX_ERR_NULL_POINTER, MVX_ERR_BAD_ENUM, MVX_ERR_BAD_SHAPE = -1, -2, -3
 MVX_ERR_WORKSPACE, MVX_ERR_CUDA, MVX_ERR_UNSUPPORTED, MVX_ERR_DEVICE_FLAG = -4, -5, -6, -7
-MVX_F32, MVX_F64 = 0, 1
+MVX_F32, MVX_F64, MVX_U8, MVX_F16 = 0, 1, 2, 3
 DENSITY = {"gaussian": 0, "binary": 1}
 RADII = {"scalar": 0, "channel-wise": 1, "atom-wise": 2}
 MODE = {"single": 0, "types": 1, "features": 2}
@@ -62,6 +62,7 @@ class Batch(ctypes.Structure):
         ("max_radius", ctypes.c_double),
         ("transforms", ctypes.c_void_p),
         ("out_dtype", ctypes.c_int32),
+        ("features_dtype", ctypes.c_int32),
     ]
 
 

@@ -53,7 +53,7 @@ struct Plan {
     int form;        // voxelize kernel form, see enum Form
     int ncell;
     int nlayers, zl, es4;
-    size_t off_lent, off_lbins, off_tdesc, off_kcnt, off_lids;   // kcnt: key counts, then key cursors
+    size_t off_lent, off_lbins, off_tdesc, off_kcnt, off_lids, off_wide;   // off_wide: compact features widened to fp32   // kcnt: key counts, then key cursors
     int pipe_sc;   // pipelined form: largest tile (entries) it takes
     int pipe_q;    // ... float4 words of its shared-memory ring
     bool pipe_multi;   // ... with the hit-weight cache (several channel chunks per cell)
@@ -78,6 +78,7 @@ int check_args(const mvx_grid_spec* s, const mvx_batch* b) {
         return fail(MVX_ERR_BAD_SHAPE, "Output channel is less than number of types");
     if (b->mode != MVX_MODE_TYPES && b->out_channels != C) return fail(MVX_ERR_BAD_SHAPE, "Output grid dimension incorrect");
     if (b->out_dtype < MVX_OUT_F32 || b->out_dtype > MVX_OUT_F64) return fail(MVX_ERR_BAD_ENUM, "out_dtype");
+    if (b->features_dtype != MVX_F32 && b->features_dtype != MVX_U8 && b->features_dtype != MVX_F16) return fail(MVX_ERR_BAD_ENUM, "features_dtype");
     if (b->num_mols > 0 && !b->mol_offsets) return fail(MVX_ERR_NULL_POINTER, "mol_offsets");
     if (b->total_atoms > 0) {
         if (!b->coords) return fail(MVX_ERR_NULL_POINTER, "coords");
@@ -226,6 +227,7 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     pl->off_alayers = off;  off += align_up(layered(pl->form) ? N * sizeof(uint32_t) : 0);
     pl->off_lists = off;    off += align_up(layered(pl->form) ? 0 : N * (size_t)pl->maxcols * sizeof(uint32_t));
     pl->off_entries = off;  off += align_up(pl->form == FORM_CELLS ? N * (size_t)pl->maxcols * sizeof(mvx::ColEntry) : 0);
+    pl->off_wide = off;     off += align_up((b->mode == MVX_MODE_FEATURES && b->features_dtype != MVX_F32) ? N * (size_t)b->num_channels * sizeof(float) : 0);
     pl->total = off;
     return MVX_OK;
 }
@@ -389,7 +391,8 @@ int mvx_launches_per_call(const mvx_grid_spec* spec, const mvx_batch* batch) {
     int nvox = (chan_feat && batch->out_dtype != MVX_OUT_F64) ? batch->num_channels : 1;
     const int nbin = layered(pl.form) ? (batch->total_atoms > 0 ? 3 : 1) : (bin_groups(batch->num_mols, pl.ncol) <= 1 ? 1 : 2);   // scan, place, build
     const int nexp = (pl.form == FORM_CELLS && batch->total_atoms > 0) ? 1 : 0;
-    return (batch->total_atoms > 0 ? 1 : 0) + nbin + nexp + nvox * (pl.form == FORM_PIPE ? 2 : 1);   // prep + bin + expand + voxelize
+    const int nwide = (batch->mode == MVX_MODE_FEATURES && batch->features_dtype != MVX_F32 && batch->total_atoms > 0) ? 1 : 0;
+    return (batch->total_atoms > 0 ? 1 : 0) + nwide + nbin + nexp + nvox * (pl.form == FORM_PIPE ? 2 : 1);   // prep + bin + expand + voxelize
 }
 
 int mvx_voxelize_form(const mvx_grid_spec* spec, const mvx_batch* batch) {
@@ -421,6 +424,17 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
     const int B = batch->num_mols;
     const int64_t N = batch->total_atoms;
     const int C = batch->mode == MVX_MODE_SINGLE ? 1 : batch->num_channels;
+    mvx_batch wide;   // compact feature rows: widened to fp32 once, everything downstream reads the fp32 copy
+    if (batch->mode == MVX_MODE_FEATURES && batch->features_dtype != MVX_F32 && N > 0) {
+        float* dst = (float*)(ws + pl.off_wide);
+        const size_t n = (size_t)N * (size_t)C;
+        mvx::mvx_widen_features_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(batch->features, batch->features_dtype == MVX_F16, n, dst);
+        MVX_CUDA_OK(cudaGetLastError());
+        wide = *batch;
+        wide.features = dst;
+        wide.features_dtype = MVX_F32;
+        batch = &wide;
+    }
     MVX_CUDA_OK(cudaMemsetAsync(status, 0, kAlign, st));
     if (layered(pl.form))   // key counts + key cursors of the layered binning
         MVX_CUDA_OK(cudaMemsetAsync(ws + pl.off_kcnt, 0, 2 * (size_t)batch->num_mols * pl.ncol * pl.nlayers * sizeof(uint32_t), st));
@@ -451,7 +465,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         lp.nzc = pl.nzc; lp.tz = pl.tz; lp.dim = spec->dimension; lp.mode = batch->mode;
         lp.C = batch->mode == MVX_MODE_FEATURES ? C : 0; lp.es4 = pl.es4;
         lp.mol_offsets = batch->mol_offsets; lp.colrange = colrange; lp.alayers = (const uint32_t*)(ws + pl.off_alayers);
-        lp.recs = recs; lp.types = batch->types; lp.features = batch->features;
+        lp.recs = recs; lp.types = batch->types; lp.features = (const float*)batch->features;
         lp.bins = bins; lp.lbins = (uint2*)(ws + pl.off_lbins);
         lp.tdesc = pl.form == FORM_PIPE ? (mvx::TileDesc*)(ws + pl.off_tdesc) : nullptr;
         lp.lent = (float4*)(ws + pl.off_lent);
@@ -507,7 +521,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         vp.dim = spec->dimension; vp.ncx = pl.geo.ncx; vp.ncol = pl.ncol; vp.nzc = pl.nzc; vp.tz = pl.tz;
         vp.C = C; vp.Cout = batch->out_channels; vp.maxcols = pl.maxcols; vp.cull = pl.geo.nb > 1;
         vp.mol_offsets = batch->mol_offsets; vp.recs = recs; vp.bins = bins; vp.lists = lists;
-        vp.types = batch->types; vp.features = batch->features; vp.chan_radii = nullptr; vp.out = out; vp.out_kind = batch->out_dtype;
+        vp.types = batch->types; vp.features = (const float*)batch->features; vp.chan_radii = nullptr; vp.out = out; vp.out_kind = batch->out_dtype;
         vp.entries = entries; vp.masks = legacy_masks;
         vp.nlayers = pl.nlayers; vp.zl = pl.zl; vp.es4 = pl.es4;
         vp.lent = (const float4*)(ws + pl.off_lent);
@@ -525,7 +539,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
             fp.Cout = batch->out_channels; fp.maxcols = pl.maxcols; fp.binary = binary;
             fp.scalar_radius = spec->radii_type == MVX_RADII_SCALAR;
             fp.mol_offsets = batch->mol_offsets; fp.recs = recs; fp.bins = bins; fp.lists = lists;
-            fp.types = batch->types; fp.features = batch->features; fp.chan_radii = chan_feat ? batch->radii : nullptr;
+            fp.types = batch->types; fp.features = (const float*)batch->features; fp.chan_radii = chan_feat ? batch->radii : nullptr;
             fp.out = (double*)out;
             const unsigned long long nb64 = (unsigned long long)B * pl.ncol;
             if (nb64 > 0x7fffffffULL) return fail(MVX_ERR_BAD_SHAPE, "batch too large for one launch; split it");
@@ -591,6 +605,7 @@ int mvx_check_status(void* workspace, void* stream) {
 }
 
 namespace {
+size_t feature_bytes(int dtype) { return dtype == MVX_U8 ? 1 : (dtype == MVX_F16 ? 2 : 4); }
 struct Staging { size_t off_offs, off_coords, off_centers, off_types, off_features, off_radii, off_transforms, total; };
 void plan_staging(const mvx_grid_spec* s, const mvx_batch* b, Staging* sg) {
     const size_t N = (size_t)b->total_atoms, B = (size_t)b->num_mols;
@@ -600,7 +615,7 @@ void plan_staging(const mvx_grid_spec* s, const mvx_batch* b, Staging* sg) {
     sg->off_coords = off;   off += align_up(N * 3 * (b->coords_dtype == MVX_F64 ? 8 : 4));
     sg->off_centers = off;  off += align_up(b->centers ? B * 3 * (b->centers_dtype == MVX_F64 ? 8 : 4) : 0);
     sg->off_types = off;    off += align_up(b->mode == MVX_MODE_TYPES ? N * sizeof(int32_t) : 0);
-    sg->off_features = off; off += align_up(b->mode == MVX_MODE_FEATURES ? N * C * sizeof(float) : 0);
+    sg->off_features = off; off += align_up(b->mode == MVX_MODE_FEATURES ? N * C * feature_bytes(b->features_dtype) : 0);
     size_t nr = s->radii_type == MVX_RADII_ATOM_WISE ? N : (s->radii_type == MVX_RADII_CHANNEL_WISE ? C : 0);
     sg->off_radii = off;    off += align_up(nr * sizeof(float));
     sg->off_transforms = off; off += align_up(b->transforms ? B * 12 * sizeof(double) : 0);
@@ -649,7 +664,7 @@ int mvx_voxelize_host(const mvx_grid_spec* spec, const mvx_batch* hb, void* out,
         db.types = (const int32_t*)(dv + sg.off_types);
     }
     if (hb->mode == MVX_MODE_FEATURES && N > 0) {
-        MVX_CUDA_OK(cudaMemcpyAsync(dv + sg.off_features, hb->features, N * C * sizeof(float), cudaMemcpyHostToDevice, st));
+        MVX_CUDA_OK(cudaMemcpyAsync(dv + sg.off_features, hb->features, N * C * feature_bytes(hb->features_dtype), cudaMemcpyHostToDevice, st));
         db.features = (const float*)(dv + sg.off_features);
     }
     if (spec->radii_type != MVX_RADII_SCALAR && hb->radii) {

@@ -2085,4 +2085,11 @@ __global__ void __launch_bounds__(256) mvx_voxelize_f64_kernel(const VoxF64Param
     }
 }
 
+// Compact feature rows (u8 / f16) -> fp32, exactly: the reference's features.astype(float32) (numpy/voxelizer.py:127-128).
+__global__ void __launch_bounds__(256) mvx_widen_features_kernel(const void* __restrict__ src, int is_f16, size_t n, float* __restrict__ dst) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dst[i] = is_f16 ? __half2float(reinterpret_cast<const __half*>(src)[i]) : (float)reinterpret_cast<const unsigned char*>(src)[i];
+}
+
 }  // namespace mvx

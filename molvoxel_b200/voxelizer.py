@@ -427,7 +427,11 @@ class Voxelizer:
             if mode == "types":
                 b.types = ptr(dev(torch.as_tensor(channels), torch.int32))
             elif mode == "features":
-                b.features = ptr(dev(torch.as_tensor(channels), torch.float32))
+                ft = torch.as_tensor(channels)
+                if ft.dtype in (torch.uint8, torch.float16):   # compact rows: widened exactly on the device
+                    b.features, b.features_dtype = ptr(dev(ft, ft.dtype)), (_lib.MVX_U8 if ft.dtype == torch.uint8 else _lib.MVX_F16)
+                else:
+                    b.features = ptr(dev(ft, torch.float32))
             if self.is_radii_type_scalar:
                 b.radius = float(radii)
             else:
@@ -450,7 +454,11 @@ class Voxelizer:
                 t = channels.detach().cpu().numpy() if isinstance(channels, torch.Tensor) else np.asarray(channels)
                 b.types = ptr(host(t.astype(np.int16), np.int32))   # the reference narrows to int16 (:269)
             elif mode == "features":
-                b.features = ptr(host(channels, np.float32))
+                fa = channels.detach().cpu().numpy() if isinstance(channels, torch.Tensor) else np.asarray(channels)
+                if fa.dtype in (np.uint8, np.float16):   # compact rows cross PCIe as they are, widened exactly on the device
+                    b.features, b.features_dtype = ptr(host(fa)), (_lib.MVX_U8 if fa.dtype == np.uint8 else _lib.MVX_F16)
+                else:
+                    b.features = ptr(host(fa, np.float32))
             if self.is_radii_type_scalar:
                 b.radius = float(radii)
             else:

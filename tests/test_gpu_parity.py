@@ -637,3 +637,33 @@ def test_pipelined_form_large_grid_many_layers():
     vox.check_status()
     ref = OracleVoxelizer(res, dim, "atom-wise", "binary").forward_single(coords, np.zeros(3), radii)
     assert np.array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.float16])
+@pytest.mark.parametrize("dense", [False, True], ids=["ligands_cells", "pocket_pipe"])
+def test_compact_feature_rows_equal_fp32_rows(dtype, dense):
+    """features_dtype U8 / F16: rows are widened exactly on the device, so the grids equal those of the same
+    values passed as float32 bit for bit — host arrays (blocking and pipelined paths) and device tensors."""
+    rng = np.random.default_rng(5 + dense)
+    if dense:
+        B, V = 3, 1500
+        offs = np.arange(B + 1, dtype=np.int32) * V
+        coords = rng.uniform(-11.5, 11.5, size=(B * V, 3))
+        dim = 48
+    else:
+        offs, coords, _ = ligand_batch(rng, 9, 4)
+        dim = 32
+    N = coords.shape[0]
+    feats = rng.integers(0, 4, size=(N, 12)).astype(dtype)
+    if dtype == np.float16:
+        feats = (feats * np.float16(0.375)).astype(np.float16)
+    vox = mv.create_voxelizer(0.5, dim, "scalar", "gaussian", library="b200")
+    ref = vox.forward_features_batch(coords, offs, None, feats.astype(np.float32), 1.0).clone()
+    assert torch.equal(vox.forward_features_batch(coords, offs, None, feats, 1.0), ref)
+    assert torch.equal(vox.forward_features_batch(coords, offs, None, feats, 1.0, non_blocking=True), ref)
+    vox.check_status()
+    dev_feats = torch.from_numpy(feats).cuda()
+    assert torch.equal(vox.forward_features_batch(torch.from_numpy(coords).cuda(), torch.from_numpy(offs).cuda(), None,
+                                                  dev_feats, 1.0), ref)
+    a, b = offs[1], offs[2]
+    assert torch.equal(vox.forward_features(coords[a:b], None, feats[a:b], 1.0), ref[1])
