@@ -187,7 +187,7 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     const int layers = pl->nzc * ((tz + mvx::kCellZ - 1) / mvx::kCellZ);
     pl->ncell = layers * mvx::kCellsXY;
     pl->masks = pl->nv == 4 && pl->ncell <= 64;
-    int zl = (int)std::floor(2.0 * reach * (1.0 + 1e-6) / (mvx::kCellZ * s->resolution)) + 2;   // z layers one sphere can reach
+    int zl = (int)std::floor(2.0 * reach * (1.0 + 1e-3) / (mvx::kCellZ * s->resolution)) + 2;   // z layers one sphere can reach (prep enforces it)
     if (zl > layers) zl = layers;
     // Kernel form by density: expected entries per column = atoms * columns-per-atom / columns.
     {
@@ -451,7 +451,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         pp.recs = recs; pp.colrange = colrange; pp.status = status;
         pp.alayers = layered(pl.form) ? (uint32_t*)(ws + pl.off_alayers) : nullptr;
         pp.kcnt = layered(pl.form) ? (uint32_t*)(ws + pl.off_kcnt) : nullptr;
-        pp.nzc = pl.nzc; pp.tz = pl.tz; pp.ncol = pl.ncol; pp.nl = pl.nlayers; pp.tau_lin = pl.tau_lin; pp.tau_quad = pl.tau_quad;
+        pp.nzc = pl.nzc; pp.tz = pl.tz; pp.ncol = pl.ncol; pp.nl = pl.nlayers; pp.zl = pl.zl; pp.tau_lin = pl.tau_lin; pp.tau_quad = pl.tau_quad;
         const unsigned grid = (unsigned)((N + 255) / 256);
         mvx::mvx_prep_kernel<<<grid, 256, 0, st>>>(pp);
         MVX_CUDA_OK(cudaGetLastError());

@@ -2,14 +2,21 @@
 //
 // Path restated (semantics only; the structure is new): reference molvoxel/voxelizer/numpy/voxelizer.py
 //   prologue + clip + block cull  :263-295, :481-527   -> mvx_prep_kernel   (one thread per atom, fp64)
-//   per-block atom lists          :496-527             -> mvx_bin_kernel    (CSR column lists, prefix sum)
+//   per-block atom lists          :496-527             -> ligand batches: mvx_bin_* (CSR column lists, prefix sum) + mvx_expand_kernel
+//                                                         dense batches:  counting sort by (molecule, column, z layer):
+//                                                                         prep counts, mvx_lscan / mvx_lplace / mvx_lbuild_kernel
 //   distance / density / channel accumulation  :531-560, :344-366, :194-236, :457-477
-//                                                      -> mvx_voxelize_kernel (gather, one write per voxel)
+//                                                      -> gather kernels, every voxel written once:
+//                                                         mvx_voxelize_cells_kernel  ligand batches, one CTA per tile, HBM-write-bound
+//                                                         mvx_voxelize_pipe_kernel   dense batches, persistent, cp.async.bulk + mbarrier ring
+//                                                         mvx_voxelize_tiles_kernel / _sweep_kernel  non-persistent form on the same entries
+//                                                         mvx_voxelize_kernel        generic (any D);  mvx_voxelize_f64_kernel  precision=64
 //
-// Data layout in HBM
-//   out      (B, Cout, D, H, W) fp32, W contiguous (reference layout, numpy/voxelizer.py:60-70)
+// Data layout in HBM (DESIGN.md section 2)
+//   out      (B, Cout, D, H, W) fp32 (bf16 / fp16 / fp64 by out_dtype), W contiguous (reference layout, numpy/voxelizer.py:60-70)
 //   AtomRec  40 B per atom: centred fp64 position, fp32 radius, cull "forbidden planes", z voxel range
-//   lists    uint32 atom ids per (molecule, 8x8 voxel column), ascending = the reference's atom order
+//   lists    uint32 atom ids per (molecule, 8x8 voxel column), ascending = the reference's atom order (ligand batches)
+//   lent     layered entries per (molecule, column, 16-voxel z layer), record + feature row, ascending atom order (dense batches)
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -67,7 +74,7 @@ struct PrepParams {
     // cutoff sphere reaches; nullptr otherwise
     uint32_t* alayers;
     uint32_t* kcnt;     // layered forms: atoms per (molecule, column, layer), counted here with fire-and-forget atomics
-    int nzc, tz, ncol, nl;
+    int nzc, tz, ncol, nl, zl;   // zl: layers reserved per atom
     float tau_lin, tau_quad;
 };
 
@@ -267,6 +274,10 @@ __global__ void __launch_bounds__(256) mvx_prep_kernel(const PrepParams P) {
                     if (ez * ez <= lim) m |= 1u << (zc * ncz_max + cz);
                 }
             }
+        }
+        if (__popc(m) > P.zl) {   // more layers than the workspace reserves per atom: a radius above max_radius
+            atomicOr(P.status, kFlagRadiusOverMax);
+            while (__popc(m) > P.zl) m &= m - 1u;
         }
         P.alayers[n] = m;
         if (m != 0u) {   // keep is true: count this atom under every (column, layer) key it belongs to

@@ -667,3 +667,27 @@ def test_compact_feature_rows_equal_fp32_rows(dtype, dense):
                                                   dev_feats, 1.0), ref)
     a, b = offs[1], offs[2]
     assert torch.equal(vox.forward_features(coords[a:b], None, feats[a:b], 1.0), ref[1])
+
+
+@pytest.mark.parametrize("V,dim", [(60, 32), (2500, 40)], ids=["ligand_cells", "dense_pipe"])
+def test_understated_max_radius_is_flagged_not_overrun(V, dim):
+    """max_radius sizes the per-atom column / layer reserve of the workspace.  A caller that understates it gets a
+    ValueError from the device-side check (radius over max), never writes outside the reserve (guard bands intact)."""
+    rng = np.random.default_rng(V)
+    half = 0.5 * (dim - 1) / 2
+    coords = rng.uniform(-half, half, size=(V, 3))
+    feats = rng.uniform(size=(V, 8)).astype(np.float32)
+    radii = np.full(V, 1.0, dtype=np.float32)
+    radii[V // 2] = 9.0                                         # reaches far more columns / layers than max_radius = 1 reserves
+    vox = mv.create_voxelizer(0.5, dim, "atom-wise", "gaussian", library="b200")
+    vox.forward_features(coords, None, feats, np.ones(V, dtype=np.float32))   # sizes the workspace
+    ws_bytes = vox._ws.numel()
+    guard = 1 << 16
+    big_ws = torch.full((ws_bytes + 2 * guard,), 0xA5, dtype=torch.uint8, device="cuda")
+    vox._ws = big_ws[guard:guard + ws_bytes]
+    t = lambda a: torch.from_numpy(a).cuda()   # noqa: E731
+    vox._forward_batch("features", t(coords), t(np.array([0, V], dtype=np.int32)), None, t(feats), t(radii), 8, 0.0, False,
+                       None, max_radius=1.0)
+    with pytest.raises(ValueError):
+        vox.check_status()
+    assert bool((big_ws[:guard] == 0xA5).all()) and bool((big_ws[guard + ws_bytes:] == 0xA5).all())
