@@ -1635,12 +1635,21 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   //
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0u;
 }
-// Bounded wait: a pipeline bug traps (the launch fails with an error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 16)) __trap();
+// Bounded wait: a pipeline bug traps (the launch fails with an error) instead of hanging the GPU.  The bound is wall
+// time (20 s on %globaltimer, looked at every 4096 failed attempts), so time-slicing with other contexts cannot trip it.
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (uint32_t spins = 1;; ++spins) {
+        if (mbar_try_wait(bar, parity)) return;
+        if ((spins & 4095u) == 0u) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > 20000000000ull) __trap();
+        }
     }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 // global -> shared bulk copy (bytes % 16 == 0, both addresses 16-byte aligned); completion counts on `bar`
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
