@@ -187,7 +187,10 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     const int layers = pl->nzc * ((tz + mvx::kCellZ - 1) / mvx::kCellZ);
     pl->ncell = layers * mvx::kCellsXY;
     pl->masks = pl->nv == 4 && pl->ncell <= 64;
-    int zl = (int)std::floor(2.0 * reach * (1.0 + 1e-3) / (mvx::kCellZ * s->resolution)) + 2;   // z layers one sphere can reach (prep enforces it)
+    // z layers one cutoff sphere can reach (prep enforces it): a span of S voxels touches at most floor(S / 16) + 2 full
+    // layers, plus one more per z-chunk end inside the span when chunks end in a short layer (tz % 16 != 0)
+    const double span_vox = 2.0 * reach * (1.0 + 1e-3) / s->resolution;
+    int zl = (int)std::floor(span_vox / mvx::kCellZ) + 2 + ((tz % mvx::kCellZ) != 0 ? (int)std::floor(span_vox / tz) + 1 : 0);
     if (zl > layers) zl = layers;
     // Kernel form by density: expected entries per column = atoms * columns-per-atom / columns.
     {
