@@ -697,3 +697,72 @@ def test_understated_max_radius_is_flagged_not_overrun(V, dim):
     with pytest.raises(ValueError):
         vox.check_status()
     assert bool((big_ws[:guard] == 0xA5).all()) and bool((big_ws[guard + ws_bytes:] == 0xA5).all())
+
+
+@pytest.mark.parametrize("kernel", [None, "pipe", "tiles"], ids=["auto", "pipe", "tiles"])
+@pytest.mark.parametrize("seed", list(range(int(__import__("os").environ.get("MVX_DENSE_FUZZ_SEEDS", "10")))))
+def test_randomized_dense_configs_vs_oracle(seed, kernel, monkeypatch):
+    """Differential fuzz of the dense regime: hundreds to thousands of atoms per molecule, uniform + clustered (tiles
+    that overflow the ring go to the sweep kernel), up to 40 channels (several channel chunks: hit-weight cache),
+    odd z extents (short layers), reduced-precision output now and then."""
+    if kernel is not None:
+        monkeypatch.setenv("MVX_KERNEL", kernel)
+    rng = np.random.default_rng(7000 + seed)
+    dim = int(rng.choice([32, 40, 48, 52, 64, 72, 96]))
+    res = float(rng.choice([0.375, 0.5, 0.6]))
+    mode = str(rng.choice(["types", "features", "features", "single"]))
+    density = str(rng.choice(["gaussian", "binary"]))
+    radii_type = str(rng.choice(["scalar", "atom-wise"] if mode == "single" else ["scalar", "atom-wise", "channel-wise"]))
+    bd = [None, 8, 16, dim][int(rng.integers(0, 4))]
+    C = 1 if mode == "single" else int(rng.choice([3, 9, 16, 20, 33, 40]))
+    B = int(rng.integers(1, 4))
+    half = res * (dim - 1) / 2
+    counts, chunks = [], []
+    for _ in range(B):
+        nu, nc = int(rng.integers(300, 3000 if dim <= 64 else 6000)), int(rng.choice([0, 0, 400, 1200]))
+        c = rng.uniform(-half - 1, half + 1, size=(nu, 3))
+        if nc:
+            c = np.concatenate([c, rng.normal(scale=0.8, size=(nc, 3)) + rng.uniform(-half / 2, half / 2, size=3)])
+            rng.shuffle(c)
+        chunks.append(c)
+        counts.append(len(c))
+    offs = np.zeros(B + 1, dtype=np.int32)
+    offs[1:] = np.cumsum(counts)
+    coords = np.concatenate(chunks)
+    N = int(offs[-1])
+    centers = None if rng.uniform() < 0.5 else rng.normal(scale=0.4, size=(B, 3))
+    rmax = float(rng.uniform(0.8, 2.2))
+    if radii_type == "scalar":
+        radii = rmax
+    elif radii_type == "atom-wise":
+        radii = rng.uniform(0.5 * rmax, rmax, size=N).astype(np.float32)
+    else:
+        radii = rng.uniform(0.5 * rmax, rmax, size=C).astype(np.float32)
+    types = rng.integers(0, C, size=N).astype(np.int32) if mode == "types" else None
+    feats = rng.integers(0, 4, size=(N, C)).astype(np.float32) if mode == "features" else None   # exact fp32 sums
+    vox = mv.create_voxelizer(res, dim, radii_type, density, library="b200", blockdim=bd)
+    if mode == "types":
+        out = vox.forward_types_batch(coords, offs, centers, types, radii, C)
+    elif mode == "features":
+        out = vox.forward_features_batch(coords, offs, centers, feats, radii)
+    else:
+        out = vox.forward_single_batch(coords, offs, centers, radii)
+    vox.check_status()
+    ref = oracle_forward_batch(res, dim, radii_type, density, 0.5, bd or 8, mode, offs, coords, centers, types, feats,
+                               C, radii, num_threads=8)
+    got = out.cpu().numpy()
+    if density == "binary":
+        assert np.array_equal(got, ref), f"{(got != ref).sum()} voxels differ"
+    else:
+        peak = max(1.0, float(np.abs(ref).max()))
+        assert np.array_equal(got != 0, ref != 0)
+        assert float(np.abs(got - ref).max()) <= 8 * GAUSS_TOL * peak
+    if seed % 3 == 0:   # bf16 grid == the fp32 grid rounded once
+        low = mv.create_voxelizer(res, dim, radii_type, density, library="b200", blockdim=bd, out_dtype=torch.bfloat16)
+        if mode == "types":
+            lo = low.forward_types_batch(coords, offs, centers, types, radii, C)
+        elif mode == "features":
+            lo = low.forward_features_batch(coords, offs, centers, feats, radii)
+        else:
+            lo = low.forward_single_batch(coords, offs, centers, radii)
+        assert torch.equal(out.to(torch.bfloat16), lo)
