@@ -34,6 +34,8 @@ WORKLOADS = {
                  desc="binary-density forward_types 4 channels, 64^3, 1,024 ligands (~50 atoms)"),
     "cfg2": dict(mode="features", C=16, dim=48, res=0.5, density="gaussian", radii_type="scalar", atoms=(2000, 2000), batch=256,
                  desc="synthetic protein pocket 2,000 atoms, forward_features C=16 (8 one-hot + 8 Bernoulli(0.25)), 48^3, gaussian, batch 256"),
+    "cfg2b": dict(mode="features", C=16, dim=48, res=0.5, density="gaussian", radii_type="scalar", atoms=(2000, 2000), batch=256,
+                  desc="cfg2 with the atoms in a Gaussian blob (sigma 4 A) instead of uniform: heterogeneous tiles (not a BASELINE config)"),
     "cfg5": dict(mode="features", C=32, dim=96, res=0.375, density="gaussian", radii_type="atom-wise", atoms=(10000, 10000), batch=16,
                  desc="large complex 10,000 atoms, forward_features C=32 dense, 96^3, res 0.375, atom-wise radii U[1,2]"),
 }
@@ -67,11 +69,13 @@ def make_batch(name: str, B: int, seed: int):
     else:           # pocket / complex: uniform in the grid cube
         half = w["res"] * (w["dim"] - 1) / 2.0
         xyz = rng.uniform(-half, half, size=(N, 3))
+        if name == "cfg2b":
+            xyz = np.clip(rng.normal(scale=4.0, size=(N, 3)), -half, half)
     coords = xyz.astype(np.float32).astype(np.float64)
     out = dict(offs=offs, coords=coords, centers=np.zeros((B, 3)), types=None, feats=None, radii=1.0)
     if w["mode"] == "types":
         out["types"] = rng.integers(0, w["C"], size=N).astype(np.int32)
-    elif name == "cfg2":
+    elif name in ("cfg2", "cfg2b"):
         f = np.zeros((N, 16), dtype=np.float32)
         f[np.arange(N), rng.integers(0, 8, size=N)] = 1.0
         f[:, 8:] = (rng.uniform(size=(N, 8)) < 0.25).astype(np.float32)
@@ -136,7 +140,7 @@ def time_reference(name, steps, warmup, library="numpy", procs=None, per_core=No
     w = WORKLOADS[name]
     cores = procs or host_cores()
     if per_core is None:
-        per_core = {"cfg4": 64, "cfg3": 64, "cfg2": 8, "cfg5": 1}[name]
+        per_core = {"cfg4": 64, "cfg3": 64, "cfg2": 8, "cfg2b": 8, "cfg5": 1}[name]
     sample = cores * per_core
     jobs = _jobs(make_batch(name, sample, seed=1234), w)
     ctx = mp.get_context("fork")
@@ -169,7 +173,7 @@ def time_oracle_port(name, steps, warmup, per_core=None):
     w = WORKLOADS[name]
     cores = host_cores()
     if per_core is None:
-        per_core = {"cfg4": 16, "cfg3": 16, "cfg2": 4, "cfg5": 1}[name]
+        per_core = {"cfg4": 16, "cfg3": 16, "cfg2": 4, "cfg2b": 4, "cfg5": 1}[name]
     sample = min(cores * per_core, max(cores, int(6e9 // (4 * w["C"] * w["dim"] ** 3))))
     b = make_batch(name, sample, seed=1234)
     run = lambda: oracle_forward_batch(w["res"], w["dim"], w["radii_type"], w["density"], 0.5, 8, w["mode"], b["offs"],  # noqa: E731
@@ -516,7 +520,7 @@ def cpu_baseline_subprocess(name):
 def cpu_baseline_worker(name):
     res = {}
     detail = {}
-    n1 = {"cfg4": 64, "cfg3": 64, "cfg2": 6, "cfg5": 2}[name]
+    n1 = {"cfg4": 64, "cfg3": 64, "cfg2": 6, "cfg2b": 6, "cfg5": 2}[name]
     if reference_available():
         res = time_reference(name, steps=4, warmup=1, library="numpy")
         detail["numpy_1core_mol_per_s"] = time_reference_single_core(name, "numpy", n1)
@@ -557,7 +561,7 @@ def main():
     global ATOMS_OVERRIDE
     ATOMS_OVERRIDE = max(0, args.atoms)
     if args.steps <= 0:
-        args.steps = {"cfg4": 200, "cfg3": 300, "cfg2": 300, "cfg5": 100}[args.workload] if args.impl == "b200" else 5
+        args.steps = {"cfg4": 200, "cfg3": 300, "cfg2": 300, "cfg2b": 300, "cfg5": 100}[args.workload] if args.impl == "b200" else 5
     if args.cpu_baseline_worker:
         return cpu_baseline_worker(args.workload)
     if args.impl == "reference":
