@@ -393,7 +393,7 @@ int mvx_launches_per_call(const mvx_grid_spec* spec, const mvx_batch* batch) {
     const bool chan_feat = batch->mode == MVX_MODE_FEATURES && spec->radii_type == MVX_RADII_CHANNEL_WISE;
     int nvox = (chan_feat && batch->out_dtype != MVX_OUT_F64) ? batch->num_channels : 1;
     const int nbin = layered(pl.form) ? (batch->total_atoms > 0 ? 3 : 1) : (bin_groups(batch->num_mols, pl.ncol) <= 1 ? 1 : 2);   // scan, place, build
-    const int nexp = (pl.form == FORM_CELLS && batch->total_atoms > 0) ? 1 : 0;
+    const int nexp = (pl.form == FORM_CELLS && batch->total_atoms > 0 && bin_groups(batch->num_mols, pl.ncol) > 1) ? 1 : 0;   // fused into bin for big batches
     const int nwide = (batch->mode == MVX_MODE_FEATURES && batch->features_dtype != MVX_F32 && batch->total_atoms > 0) ? 1 : 0;
     return (batch->total_atoms > 0 ? 1 : 0) + nwide + nbin + nexp + nvox * (pl.form == FORM_PIPE ? 2 : 1);   // prep + bin + expand + voxelize
 }
@@ -495,7 +495,17 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         bp.mol_offsets = batch->mol_offsets; bp.colrange = colrange; bp.bins = bins; bp.lists = lists;
         const size_t smem = 2 * (size_t)pl.ncol * sizeof(uint32_t);
         const int groups = bin_groups(B, pl.ncol);
-        if (groups <= 1) {
+        mvx::ExpandParams ep;   // column lists -> staged-ready entries (CELLS form)
+        ep.res = pl.geo.res; ep.half_width = pl.geo.half_width; ep.sigma = spec->sigma;
+        ep.tau_lin = pl.tau_lin; ep.tau_quad = pl.tau_quad;
+        ep.dim = spec->dimension; ep.ncx = pl.geo.ncx; ep.ncol = pl.ncol; ep.nzc = pl.nzc; ep.tz = pl.tz;
+        ep.maxcols = pl.maxcols; ep.mode = batch->mode; ep.masks = legacy_masks; ep.B = B;
+        ep.mol_offsets = batch->mol_offsets; ep.recs = recs; ep.bins = bins; ep.lists = lists;
+        ep.types = batch->types; ep.entries = entries;
+        const bool expand = pl.form == FORM_CELLS && N > 0;
+        if (groups <= 1 && expand) {   // many small molecules: bin and expand in one launch
+            mvx::mvx_bin_expand_kernel<<<(unsigned)B, 256, smem, st>>>(bp, ep);
+        } else if (groups <= 1) {
             mvx::mvx_bin_kernel<<<(unsigned)B, 256, smem, st>>>(bp);
         } else {   // few large molecules: spread each molecule's columns over several CTAs
             mvx::mvx_bin_count_kernel<<<(unsigned)(B * groups), 256, 0, st>>>(bp, groups);
@@ -503,14 +513,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
             mvx::mvx_bin_fill_kernel<<<(unsigned)(B * groups), 256, smem, st>>>(bp, groups);
         }
         MVX_CUDA_OK(cudaGetLastError());
-        if (pl.form == FORM_CELLS && N > 0) {   // column lists -> staged-ready entries
-            mvx::ExpandParams ep;
-            ep.res = pl.geo.res; ep.half_width = pl.geo.half_width; ep.sigma = spec->sigma;
-            ep.tau_lin = pl.tau_lin; ep.tau_quad = pl.tau_quad;
-            ep.dim = spec->dimension; ep.ncx = pl.geo.ncx; ep.ncol = pl.ncol; ep.nzc = pl.nzc; ep.tz = pl.tz;
-            ep.maxcols = pl.maxcols; ep.mode = batch->mode; ep.masks = legacy_masks; ep.B = B;
-            ep.mol_offsets = batch->mol_offsets; ep.recs = recs; ep.bins = bins; ep.lists = lists;
-            ep.types = batch->types; ep.entries = entries;
+        if (expand && groups > 1) {
             const long long warps = (long long)B * pl.ncol;
             mvx::mvx_expand_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(ep);
             MVX_CUDA_OK(cudaGetLastError());

@@ -406,12 +406,8 @@ __global__ void mvx_bin_fill_kernel(const BinParams P, int groups) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kExpandSmemMasks = 512;   // masks of the first 512 entries of a column stay in shared memory
 
-__global__ void __launch_bounds__(256) mvx_expand_kernel(const ExpandParams P) {
-    const int lane = threadIdx.x & 31;
-    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (gw >= (long long)P.B * P.ncol) return;
-    const int mol = (int)(gw / P.ncol), col = (int)(gw % P.ncol);
-    const uint2 bin = P.bins[gw];
+// One column's list -> ColEntry records, by one warp (lane = list entry).
+__device__ __forceinline__ void expand_column(const ExpandParams& P, const int mol, const int col, const uint2 bin, const int lane) {
     if (bin.y == 0) return;
     const size_t base = (size_t)P.mol_offsets[mol] * (size_t)P.maxcols + bin.x;
     const int x0 = (col / P.ncx) * kTile, y0 = (col % P.ncx) * kTile;
@@ -468,6 +464,40 @@ __global__ void __launch_bounds__(256) mvx_expand_kernel(const ExpandParams P) {
         float4* dst = reinterpret_cast<float4*>(P.entries + base + i);
         const float4* src = reinterpret_cast<const float4*>(&e);
         dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    }
+}
+
+__global__ void __launch_bounds__(256) mvx_expand_kernel(const ExpandParams P) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gw >= (long long)P.B * P.ncol) return;
+    expand_column(P, (int)(gw / P.ncol), (int)(gw % P.ncol), P.bins[gw], lane);
+}
+
+// Fused form for many small molecules (ligand batches): one CTA per molecule counts, scans, fills its column lists and
+// expands each of them right away (the warp that filled a list turns it into entries), one launch instead of two.
+__global__ void mvx_bin_expand_kernel(const BinParams P, const ExpandParams E) {
+    extern __shared__ uint32_t s_u32[];
+    uint32_t* s_cnt = s_u32;            // [ncol]
+    uint32_t* s_off = s_u32 + P.ncol;   // [ncol]
+    const int mol = blockIdx.x;
+    const int a0 = P.mol_offsets[mol], V = P.mol_offsets[mol + 1] - a0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t* cr = P.colrange + a0;
+    for (int col = warp; col < P.ncol; col += nwarps) {
+        const uint32_t cnt = bin_scan_column(cr, V, col / P.ncx, col % P.ncx, lane, nullptr, 0, a0);
+        if (lane == 0) s_cnt[col] = cnt;
+    }
+    __syncthreads();
+    if (warp == 0) bin_scan_counts(s_cnt, s_off, P.ncol, lane);
+    __syncthreads();
+    uint32_t* seg = P.lists + (size_t)a0 * (size_t)P.maxcols;
+    for (int col = warp; col < P.ncol; col += nwarps) {
+        const uint2 bin = make_uint2(s_off[col], s_cnt[col]);
+        if (bin.y != 0) bin_scan_column(cr, V, col / P.ncx, col % P.ncx, lane, seg, bin.x, a0);
+        if (lane == 0) P.bins[(size_t)mol * P.ncol + col] = bin;
+        __syncwarp();   // the list written by this warp's lanes is read back by other lanes below
+        expand_column(E, mol, col, bin, lane);
     }
 }
 

@@ -40,7 +40,7 @@ def test_workspace_planning_is_host_only():
     assert L.mvx_workspace_bytes(ctypes.byref(spec), ctypes.byref(b), ctypes.byref(need)) == 0
     # 40 B record + 4 B column range + 4 columns x 4 B list entries per atom, 8 B per (molecule, column) bin
     assert need.value >= 100_000 * (40 + 4 + 16 + 4 * 48) + 2048 * 64 * 8
-    assert L.mvx_launches_per_call(ctypes.byref(spec), ctypes.byref(b)) == 4   # prep, bin, expand, voxelize
+    assert L.mvx_launches_per_call(ctypes.byref(spec), ctypes.byref(b)) == 3   # prep, bin + expand (fused), voxelize
     assert L.mvx_voxelize_form(ctypes.byref(spec), ctypes.byref(b)) == 1        # ligand batch: warp-cell form
 
 
