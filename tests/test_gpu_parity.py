@@ -766,3 +766,50 @@ def test_randomized_dense_configs_vs_oracle(seed, kernel, monkeypatch):
         else:
             lo = low.forward_single_batch(coords, offs, centers, radii)
         assert torch.equal(out.to(torch.bfloat16), lo)
+
+
+def test_size_independent_properties_cfg5_shape():
+    """BASELINE cfg 5 at full molecule size (10,000 atoms, C=32, 96^3, res 0.375, atom-wise radii; B=3): determinism,
+    batch element == single call, translation invariance, channel-permutation equivariance."""
+    rng = np.random.default_rng(55)
+    B, V, C = 3, 10000, 32
+    half = 0.375 * 95 / 2
+    coords = rng.uniform(-half, half, size=(B * V, 3)).astype(np.float32).astype(np.float64)
+    offs = np.arange(B + 1, dtype=np.int32) * V
+    feats = rng.uniform(0, 1, size=(B * V, C)).astype(np.float32)
+    radii = rng.uniform(1.0, 2.0, size=B * V).astype(np.float32)
+    vox = mv.create_voxelizer(0.375, 96, "atom-wise", "gaussian", library="b200")
+    out = vox.forward_features_batch(coords, offs, None, feats, radii)
+    assert torch.equal(out, vox.forward_features_batch(coords, offs, None, feats, radii))
+    shift = np.array([3.0, -1.25, 0.5])
+    assert torch.equal(out, vox.forward_features_batch(coords + shift, offs, np.tile(shift, (B, 1)), feats, radii))
+    a, b = offs[1], offs[2]
+    assert torch.equal(vox.forward_features(coords[a:b], None, feats[a:b], radii[a:b]), out[1])
+    perm = rng.permutation(C)   # channels are independent sums: permuting feature columns permutes grid channels, bit for bit
+    assert torch.equal(vox.forward_features_batch(coords, offs, None, np.ascontiguousarray(feats[:, perm]), radii),
+                       out[:, torch.from_numpy(perm).cuda()])
+
+
+def test_sharded_batches_equal_the_whole_batch():
+    """molecules are independent, so voxelizing the slices of shard_batch (what each rank does) and
+    concatenating equals voxelizing the whole batch, bit for bit — ligand and dense forms."""
+    from molvoxel_b200 import shard_batch
+    rng = np.random.default_rng(8)
+    for dense in (False, True):
+        if dense:
+            B, V = 6, 1500
+            offs = np.arange(B + 1, dtype=np.int32) * V
+            coords = rng.uniform(-11.5, 11.5, size=(B * V, 3))
+            dim = 48
+        else:
+            offs, coords, _ = ligand_batch(rng, 37, 4)
+            B, dim = 37, 48
+        types = rng.integers(0, 6, size=coords.shape[0]).astype(np.int32)
+        centers = rng.normal(scale=0.3, size=(B, 3))
+        vox = mv.create_voxelizer(0.5, dim, "scalar", "gaussian", library="b200")
+        whole = vox.forward_types_batch(coords, offs, centers, types, 1.1, 6).clone()
+        parts = []
+        for rank in range(3):
+            lo, (c, t), (z,) = shard_batch(offs, rank, 3, coords, types, per_mol=(centers,))
+            parts.append(vox.forward_types_batch(c, lo, z, t, 1.1, 6).clone())
+        assert torch.equal(torch.cat(parts, 0), whole)
