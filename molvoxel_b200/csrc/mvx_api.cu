@@ -611,6 +611,24 @@ int mvx_check_status(void* workspace, void* stream) {
 }
 
 namespace {
+// Pinned host block for packing the inputs of small host calls (one per calling thread, grown on demand; falls back to
+// per-array copies when page-locking fails).
+constexpr size_t kPackBytes = 1u << 20;
+struct HostPack {
+    char* p = nullptr;
+    size_t cap = 0;
+    char* get(size_t bytes) {
+        if (bytes > cap) {
+            if (p != nullptr) cudaFreeHost(p);
+            p = nullptr; cap = 0;
+            const size_t want = bytes < 65536 ? 65536 : bytes;
+            if (cudaHostAlloc((void**)&p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); p = nullptr; return nullptr; }
+            cap = want;
+        }
+        return p;
+    }
+    ~HostPack() { if (p != nullptr) cudaFreeHost(p); }   // at thread exit; an error after context teardown is ignored
+};
 size_t feature_bytes(int dtype) { return dtype == MVX_U8 ? 1 : (dtype == MVX_F16 ? 2 : 4); }
 struct Staging { size_t off_offs, off_coords, off_centers, off_types, off_features, off_radii, off_transforms, total; };
 void plan_staging(const mvx_grid_spec* s, const mvx_batch* b, Staging* sg) {
@@ -653,37 +671,49 @@ int mvx_voxelize_host(const mvx_grid_spec* spec, const mvx_batch* hb, void* out,
     const size_t N = (size_t)hb->total_atoms, B = (size_t)hb->num_mols;
     const size_t C = hb->mode == MVX_MODE_SINGLE ? 1 : (size_t)hb->num_channels;
     mvx_batch db = *hb;
-    MVX_CUDA_OK(cudaMemcpyAsync(dv + sg.off_offs, hb->mol_offsets, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    // Small calls (the reference's one-molecule-per-call pattern): the inputs are packed into one pinned staging block
+    // and cross PCIe as ONE copy instead of up to seven pageable ones (each a synchronous driver round trip).
+    // The block is reused: this function ends with a stream synchronisation (mvx_check_status).
+    char* pack = nullptr;
+    if (sg.total <= kPackBytes) {
+        thread_local HostPack hp;
+        pack = hp.get(sg.total);
+    }
+    auto put = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+        if (bytes == 0) return cudaSuccess;
+        if (pack != nullptr) { std::memcpy(pack + off, src, bytes); return cudaSuccess; }
+        return cudaMemcpyAsync(dv + off, src, bytes, cudaMemcpyHostToDevice, st);
+    };
+    MVX_CUDA_OK(put(sg.off_offs, hb->mol_offsets, (B + 1) * sizeof(int32_t)));
     db.mol_offsets = (const int32_t*)(dv + sg.off_offs);
     if (N > 0) {
-        MVX_CUDA_OK(cudaMemcpyAsync(dv + sg.off_coords, hb->coords, N * 3 * (hb->coords_dtype == MVX_F64 ? 8 : 4),
-                                    cudaMemcpyHostToDevice, st));
+        MVX_CUDA_OK(put(sg.off_coords, hb->coords, N * 3 * (hb->coords_dtype == MVX_F64 ? 8 : 4)));
         db.coords = dv + sg.off_coords;
     }
     if (hb->centers) {
-        MVX_CUDA_OK(cudaMemcpyAsync(dv + sg.off_centers, hb->centers, B * 3 * (hb->centers_dtype == MVX_F64 ? 8 : 4),
-                                    cudaMemcpyHostToDevice, st));
+        MVX_CUDA_OK(put(sg.off_centers, hb->centers, B * 3 * (hb->centers_dtype == MVX_F64 ? 8 : 4)));
         db.centers = dv + sg.off_centers;
     }
     if (hb->mode == MVX_MODE_TYPES && N > 0) {
-        MVX_CUDA_OK(cudaMemcpyAsync(dv + sg.off_types, hb->types, N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        MVX_CUDA_OK(put(sg.off_types, hb->types, N * sizeof(int32_t)));
         db.types = (const int32_t*)(dv + sg.off_types);
     }
     if (hb->mode == MVX_MODE_FEATURES && N > 0) {
-        MVX_CUDA_OK(cudaMemcpyAsync(dv + sg.off_features, hb->features, N * C * feature_bytes(hb->features_dtype), cudaMemcpyHostToDevice, st));
+        MVX_CUDA_OK(put(sg.off_features, hb->features, N * C * feature_bytes(hb->features_dtype)));
         db.features = (const float*)(dv + sg.off_features);
     }
     if (spec->radii_type != MVX_RADII_SCALAR && hb->radii) {
         size_t nr = spec->radii_type == MVX_RADII_ATOM_WISE ? N : C;
         if (nr > 0) {
-            MVX_CUDA_OK(cudaMemcpyAsync(dv + sg.off_radii, hb->radii, nr * sizeof(float), cudaMemcpyHostToDevice, st));
+            MVX_CUDA_OK(put(sg.off_radii, hb->radii, nr * sizeof(float)));
             db.radii = (const float*)(dv + sg.off_radii);
         }
     }
     if (hb->transforms) {
-        MVX_CUDA_OK(cudaMemcpyAsync(dv + sg.off_transforms, hb->transforms, B * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+        MVX_CUDA_OK(put(sg.off_transforms, hb->transforms, B * 12 * sizeof(double)));
         db.transforms = (const double*)(dv + sg.off_transforms);
     }
+    if (pack != nullptr) MVX_CUDA_OK(cudaMemcpyAsync(dv, pack, sg.total, cudaMemcpyHostToDevice, st));
     rc = mvx_voxelize(spec, &db, out, workspace, pl.total, stream);
     if (rc != MVX_OK) return rc;
     return mvx_check_status(workspace, stream);
