@@ -13,12 +13,18 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.environ.get("MVX_SO") or os.path.join(CSRC, "libmolvoxel_b200.so")   # MVX_SO: an experimental build
-SOURCES = [os.path.join(CSRC, "mvx_api.cu")]
-HEADERS = [os.path.join(CSRC, "mvx_kernels.cuh"), os.path.join(os.path.dirname(_HERE), "include", "molvoxel_b200.h")]
+OBJ_DIR = os.path.join(CSRC, "_obj")
+API_SOURCE = os.path.join(CSRC, "mvx_api.cu")
+INST_SOURCE = os.path.join(CSRC, "mvx_vox_inst.cu")
+SOURCES = [API_SOURCE, INST_SOURCE]
+HEADERS = [os.path.join(CSRC, h) for h in ("mvx_common.cuh", "mvx_bin_kernels.cuh", "mvx_vox_kernels.cuh", "mvx_launch.cuh")] + \
+          [os.path.join(os.path.dirname(_HERE), "include", "molvoxel_b200.h")]
+# (mode, channel chunk) pairs the voxelize kernels are instantiated for (x binary / gaussian): mvx_api.cu:launch_vox
+INSTANCES = [(0, 1)] + [(m, ch) for m in (1, 2) for ch in (1, 4, 8, 12, 16)]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
 
 MVX_OK = 0
@@ -73,19 +79,45 @@ def _stale() -> bool:
     return any(os.path.exists(p) and os.path.getmtime(p) > t for p in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA library for sm_100a (nvcc cross-compiles without a GPU)."""
+def _run(cmd):
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("molvoxel_b200: nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    return proc.stderr
+
+
+def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
+    """Compile the CUDA library for sm_100a (nvcc cross-compiles without a GPU).
+
+    The API unit and one unit per (mode, channel chunk, density) instantiation of the voxelize kernels are compiled
+    in parallel, linked into a temporary file and moved into place atomically; a file lock serialises concurrent
+    builders (one process per GPU may import the package at the same time)."""
     if not force and not _stale():
         return SO_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("molvoxel_b200: nvcc not found and libmolvoxel_b200.so is missing/stale")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + SOURCES
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("molvoxel_b200: nvcc failed:\n" + proc.stdout + proc.stderr)
-    if verbose:
-        print(proc.stderr)
+    import fcntl
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    with open(os.path.join(OBJ_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not _stale():   # another process built it while this one waited
+            return SO_PATH
+        flags = NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+        jobs = [([nvcc] + flags + ["-c", API_SOURCE, "-o", os.path.join(OBJ_DIR, "mvx_api.o")])]
+        for mode, ch in INSTANCES:
+            for binary in (0, 1):
+                obj = os.path.join(OBJ_DIR, f"mvx_vox_m{mode}_c{ch}_b{binary}.o")
+                jobs.append([nvcc] + flags + [f"-DMVX_INST_MODE={mode}", f"-DMVX_INST_CH={ch}", f"-DMVX_INST_BINARY={binary}",
+                                              "-c", INST_SOURCE, "-o", obj])
+        with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
+            logs = list(pool.map(_run, jobs))
+        tmp = SO_PATH + f".tmp{os.getpid()}"
+        _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + [j[-1] for j in jobs])
+        os.replace(tmp, SO_PATH)
+        if verbose:
+            print("\n".join(logs))
     return SO_PATH
 
 

@@ -9,7 +9,8 @@
 #include <string>
 
 #include "../../include/molvoxel_b200.h"
-#include "mvx_kernels.cuh"
+#include "mvx_bin_kernels.cuh"
+#include "mvx_launch.cuh"
 
 namespace {
 
@@ -97,14 +98,8 @@ int check_args(const mvx_grid_spec* s, const mvx_batch* b) {
 
 int pick_chunk(int mode, int nchan);
 
-// Voxelize kernel forms.  All give identical results; they differ in how a tile's atoms reach the warps.
-//   CELLS  column entries (48 B) with cell masks, features gathered at staging: sparse / medium batches
-//   TILES  entries regrouped per 16-voxel z layer with their feature rows, one flat staging copy,
-//          per-layer warp filter: packed complexes (hundreds of atoms per column)
-//   ROWS   generic lock-step form (any D, scalar stores when D % 4 != 0)
-//   PIPE   the tile form made persistent: two CTAs per SM walk the tiles, staging is a bulk copy (cp.async.bulk +
-//          mbarrier) issued one tile ahead, no CTA-wide barrier in the steady state: dense batches
-enum Form { FORM_ROWS = 0, FORM_CELLS = 1, FORM_TILES = 3, FORM_PIPE = 4 };
+using mvx::FORM_ROWS; using mvx::FORM_CELLS; using mvx::FORM_TILES; using mvx::FORM_PIPE;
+using mvx::DeviceSet; using mvx::set_smem;
 
 bool layered(int form) { return form == FORM_TILES || form == FORM_PIPE; }
 
@@ -235,97 +230,9 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     return MVX_OK;
 }
 
-// The dynamic shared-memory limit is a per-device function attribute: remember which devices have it (the kernels are
-// template instantiations, so one DeviceSet per call site).
-struct DeviceSet {
-    unsigned long long bits[4] = {0, 0, 0, 0};   // devices 0..255
-    bool test_and_set(int dev) {
-        if (dev < 0 || dev > 255) return false;
-        const bool had = (bits[dev >> 6] >> (dev & 63)) & 1ull;
-        bits[dev >> 6] |= 1ull << (dev & 63);
-        return had;
-    }
-};
-
-template <typename K>
-cudaError_t set_smem(K kernel, size_t smem, DeviceSet* done = nullptr) {
-    if (done != nullptr) {
-        int dev = -1;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
-        if (done->test_and_set(dev)) return cudaSuccess;
-    }
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-}
-
-// CTAs of the persistent form: one per SM of the current device
-int pipe_grid(unsigned ntiles, unsigned* grid) {
-    static int sms[256] = {0};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 255) return -1;
-    if (sms[dev] == 0) {
-        int n = 0;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) return -1;
-        sms[dev] = n;
-    }
-    const unsigned want = (unsigned)sms[dev];
-    *grid = ntiles < want ? ntiles : want;
-    return 0;
-}
-
-template <int MODE, int CH, bool BINARY, bool O16>
-cudaError_t launch_form_out(const mvx::VoxParams& vp, int form, int nv, unsigned grid, cudaStream_t st) {
-    if (form == FORM_PIPE) {
-        constexpr size_t smem = mvx::kPipeSmemBytes;
-        static DeviceSet cfg, cfg_m, cfg_t;
-        unsigned pg = 0;
-        if (pipe_grid(grid, &pg) != 0) return cudaErrorInvalidDevice;
-        if constexpr (CH == 16) {   // several channel chunks per cell (C > 16): hit-weight cache
-            if (vp.pipe_q == mvx::pipe_ring_q(true)) {
-                cudaError_t em = set_smem(mvx::mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, true>, smem, &cfg_m);
-                if (em != cudaSuccess) return em;
-                mvx::mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, true><<<pg, mvx::kPipeThreads, smem, st>>>(vp, grid);
-            }
-        }
-        if (CH != 16 || vp.pipe_q != mvx::pipe_ring_q(true)) {
-            cudaError_t em = set_smem(mvx::mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, false>, smem, &cfg);
-            if (em != cudaSuccess) return em;
-            mvx::mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, false><<<pg, mvx::kPipeThreads, smem, st>>>(vp, grid);
-        }
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        // tiles with more entries than the pipelined form takes (usually none): a small scanning grid
-        constexpr size_t smem_t = mvx::tiles_smem_bytes<MODE>();
-        e = set_smem(mvx::mvx_voxelize_sweep_kernel<MODE, CH, BINARY, O16>, smem_t, &cfg_t);
-        if (e != cudaSuccess) return e;
-        mvx::mvx_voxelize_sweep_kernel<MODE, CH, BINARY, O16><<<2 * pg < grid ? 2 * pg : grid, mvx::kThreads, smem_t, st>>>(vp, grid);
-    } else if (form == FORM_TILES) {
-        constexpr size_t smem = mvx::tiles_smem_bytes<MODE>();
-        static DeviceSet cfg;
-        { cudaError_t e = set_smem(mvx::mvx_voxelize_tiles_kernel<MODE, CH, BINARY, O16>, smem, &cfg); if (e != cudaSuccess) return e; }
-        mvx::mvx_voxelize_tiles_kernel<MODE, CH, BINARY, O16><<<grid, mvx::kThreads, smem, st>>>(vp);
-    } else if (form == FORM_CELLS) {
-        constexpr size_t smem = mvx::cells_smem_bytes<MODE, CH>();
-        static DeviceSet cfg;
-        { cudaError_t e = set_smem(mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, O16>, smem, &cfg); if (e != cudaSuccess) return e; }
-        mvx::mvx_voxelize_cells_kernel<MODE, CH, BINARY, O16><<<grid, mvx::kThreads, smem, st>>>(vp);
-    } else if (nv == 4) {
-        mvx::mvx_voxelize_kernel<MODE, CH, BINARY, 4, O16><<<grid, mvx::kThreads, 0, st>>>(vp);
-    } else {
-        mvx::mvx_voxelize_kernel<MODE, CH, BINARY, 1, O16><<<grid, mvx::kThreads, 0, st>>>(vp);
-    }
-    return cudaGetLastError();
-}
-
-template <int MODE, int CH, bool BINARY>
-cudaError_t launch_form(const mvx::VoxParams& vp, int form, int nv, unsigned grid, cudaStream_t st) {
-    return vp.out_kind == 0 ? launch_form_out<MODE, CH, BINARY, false>(vp, form, nv, grid, st)
-                            : launch_form_out<MODE, CH, BINARY, true>(vp, form, nv, grid, st);
-}
-
 template <int MODE, int CH>
 cudaError_t launch_density(const mvx::VoxParams& vp, bool binary, int form, int nv, unsigned grid, cudaStream_t st) {
-    return binary ? launch_form<MODE, CH, true>(vp, form, nv, grid, st) : launch_form<MODE, CH, false>(vp, form, nv, grid, st);
+    return binary ? mvx::launch_form<MODE, CH, true>(vp, form, nv, grid, st) : mvx::launch_form<MODE, CH, false>(vp, form, nv, grid, st);
 }
 
 // column groups per molecule for the bin pass: 1 (fused kernel) once the batch alone gives two waves of
@@ -342,11 +249,12 @@ int pick_chunk(int mode, int nchan) {
     if (mode == MVX_MODE_SINGLE) return 1;
     if (const char* e = std::getenv("MVX_CH")) {   // experiments: force the channel chunk
         int v = std::atoi(e);
-        if (v == 1 || v == 4 || v == 8 || v == 16) return v;
+        if (v == 1 || v == 4 || v == 8 || v == 12 || v == 16) return v;
     }
     if (nchan <= 1) return 1;
     if (nchan <= 4) return 4;
     if (nchan <= 8) return 8;
+    if (nchan <= 12) return 12;   // e.g. the 9-channel ligand sweep: no dead accumulator rows
     return 16;
 }
 
@@ -357,6 +265,7 @@ cudaError_t launch_vox(int mode, int ch, const mvx::VoxParams& vp, bool binary, 
             case 1: return launch_density<1, 1>(vp, binary, form, nv, grid, st);
             case 4: return launch_density<1, 4>(vp, binary, form, nv, grid, st);
             case 8: return launch_density<1, 8>(vp, binary, form, nv, grid, st);
+            case 12: return launch_density<1, 12>(vp, binary, form, nv, grid, st);
             default: return launch_density<1, 16>(vp, binary, form, nv, grid, st);
         }
     }
@@ -364,6 +273,7 @@ cudaError_t launch_vox(int mode, int ch, const mvx::VoxParams& vp, bool binary, 
         case 1: return launch_density<2, 1>(vp, binary, form, nv, grid, st);
         case 4: return launch_density<2, 4>(vp, binary, form, nv, grid, st);
         case 8: return launch_density<2, 8>(vp, binary, form, nv, grid, st);
+        case 12: return launch_density<2, 12>(vp, binary, form, nv, grid, st);
         default: return launch_density<2, 16>(vp, binary, form, nv, grid, st);
     }
 }
