@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define MVX_VERSION 100 /* 0.1.0 */
+#define MVX_VERSION 200 /* 0.2.0 */
 
 typedef enum mvx_status {
     MVX_OK = 0,
@@ -38,6 +38,18 @@ enum { MVX_RADII_SCALAR = 0, MVX_RADII_CHANNEL_WISE = 1, MVX_RADII_ATOM_WISE = 2
 enum { MVX_MODE_SINGLE = 0, MVX_MODE_TYPES = 1, MVX_MODE_FEATURES = 2 };            /* base/voxelizer.py:121-128 */
 enum { MVX_F32 = 0, MVX_F64 = 1, MVX_U8 = 2, MVX_F16 = 3 };   /* U8 / F16: compact feature rows only */
 enum { MVX_OUT_F32 = 0, MVX_OUT_BF16 = 1, MVX_OUT_F16 = 2, MVX_OUT_F64 = 3 };   /* element type of the output grid */
+/* How the caller held the SCALAR radius.  numpy's promotion rules (NEP 50) make the reference's arithmetic depend on it:
+ * a python float is weak (fp32 division dist32 / r, fp64 clip bounds); an np.float64 scalar is strong (fp64 division and
+ * Gaussian, numpy/voxelizer.py:546-548); an np.float32 scalar demotes the python-float clip bounds to fp32 (:487-488). */
+enum { MVX_RADIUS_PYFLOAT = 0, MVX_RADIUS_NP_F64 = 1, MVX_RADIUS_NP_F32 = 2 };
+/* Random rigid transform of every reference forward_* (random_translation / random_rotation, numpy/voxelizer.py:265,
+ * numpy/transform.py:43-80), applied per molecule to the centred coordinates inside the per-atom prep kernel. */
+enum {
+    MVX_TF_ROTATE = 1,           /* rotate by a unit quaternion, with the reference's quaternion products (numpy/_quaternion.py:28-54) */
+    MVX_TF_TRANSLATE = 2,        /* add the (fp32-valued) translation (numpy/transform.py:56-59) */
+    MVX_TF_TRANSLATE_ONCE = 4    /* with ROTATE: add it once (the reference's torch backend, torch/transform.py:56-60) instead of
+                                    twice (its numpy and numba backends, numpy/transform.py:56-59) */
+};
 
 /* Constructor arguments of the reference Voxelizer (base/voxelizer.py:15-38, numpy/voxelizer.py:22-35). */
 typedef struct mvx_grid_spec {
@@ -60,7 +72,7 @@ typedef struct mvx_grid_spec {
  *   features (N,C)  f32      feature rows, FEATURES            (:110); u8 | f16 rows with features_dtype
  *   radius   python-float scalar when radii_type is SCALAR
  *   radii    (C,) f32 channel-wise | (N,) f32 atom-wise        (:111)
- *   transforms (B,12) f64 optional rigid transform per molecule (:265)
+ *   transforms (B,7) f64 optional explicit rigid transform per molecule (:265): quaternion q0..q3, translation
  */
 typedef struct mvx_batch {
     int32_t        mode;            /* MVX_MODE_* */
@@ -80,11 +92,13 @@ typedef struct mvx_batch {
     double         max_radius;      /* host-known upper bound of every radius in `radii` (array
                                        radii types).  For FEATURES + channel-wise it must be the
                                        exact max: the reference clips with radii.max() (:138). */
-    const double  *transforms;      /* (B,12) f64 or NULL: per molecule a row-major 3x3 rotation R then a
-                                       translation t, applied to the centred coordinates as R.p + t before
-                                       the clip — the random rigid transform every reference forward_* takes
-                                       (random_translation / random_rotation, numpy/voxelizer.py:265,
-                                       numpy/transform.py:43-80), fused into the per-atom prep kernel. */
+    const double  *transforms;      /* (B,7) f64 or NULL: per molecule a unit quaternion (q0, q1, q2, q3) and a
+                                       translation (tx, ty, tz) — explicit parameters of the rigid transform
+                                       selected by transform_flags (e.g. drawn on the host from numpy's global
+                                       RNG in the reference's order).  NULL with transform_flags != 0: the
+                                       parameters are drawn ON THE DEVICE from a counter-based generator
+                                       (Philox4x32-10) keyed by (rng_seed, rng_offset + molecule index), so any
+                                       sharding or chunking of a sweep gives the same augmentation. */
     int32_t        out_dtype;       /* MVX_OUT_F32 (the reference's precision=32 layout, default) or a
                                        reduced-precision grid: every voxel is computed in fp32 exactly as
                                        for MVX_OUT_F32 and rounded once (nearest-even) on the store.
@@ -94,6 +108,12 @@ typedef struct mvx_batch {
                                        (one-hot / flag / count features) are widened to fp32 on the device, exactly —
                                        the reference's features.astype(float32) (numpy/voxelizer.py:127-128) — so a
                                        host caller moves 1/4 or 1/2 of the bytes over PCIe. */
+    int32_t        radius_kind;     /* MVX_RADIUS_*: how the scalar `radius` was typed by the caller (default python float) */
+    int32_t        transform_flags; /* MVX_TF_* bits; 0 = no transform (transforms is then ignored) */
+    uint64_t       rng_seed;        /* device-drawn transforms: generator key ... */
+    uint64_t       rng_offset;      /* ... and global index of this batch's first molecule */
+    double         random_translation;   /* device-drawn transforms: translation ~ U(-t, t)^3, rounded to fp32
+                                            (numpy/transform.py:74-76) */
 } mvx_batch;
 
 /* Bytes of device workspace mvx_voxelize needs for this spec/batch (256-byte aligned base). */
@@ -135,6 +155,14 @@ int mvx_voxelize_form(const mvx_grid_spec *spec, const mvx_batch *batch);
  */
 int mvx_profile_begin(int max_calls);
 int mvx_profile_end(double *ms_prep, double *ms_bin, double *ms_voxelize, int *num_calls);
+
+/*
+ * The rigid transforms mvx_voxelize draws on the device for molecules [rng_offset, rng_offset + num_mols) with these
+ * (rng_seed, transform_flags, random_translation): writes (num_mols, 7) f64 rows (quaternion, translation) to the
+ * DEVICE buffer `out` on `stream`.  Passing them back as mvx_batch.transforms gives bit-identical grids.
+ */
+int mvx_random_transforms(uint64_t rng_seed, uint64_t rng_offset, int32_t num_mols, int32_t transform_flags,
+                          double random_translation, double *out, void *stream);
 
 const char *mvx_last_error(void);
 int mvx_version(void);

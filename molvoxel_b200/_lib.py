@@ -36,6 +36,8 @@ RADII = {"scalar": 0, "channel-wise": 1, "atom-wise": 2}
 MODE = {"single": 0, "types": 1, "features": 2}
 FORM_KERNEL = {0: "mvx_voxelize_kernel", 1: "mvx_voxelize_cells_kernel", 3: "mvx_voxelize_tiles_kernel", 4: "mvx_voxelize_pipe_kernel"}
 OUT_DTYPE = {"float32": 0, "bfloat16": 1, "float16": 2, "float64": 3}
+RADIUS_PYFLOAT, RADIUS_NP_F64, RADIUS_NP_F32 = 0, 1, 2
+TF_ROTATE, TF_TRANSLATE, TF_TRANSLATE_ONCE = 1, 2, 4
 
 
 class GridSpec(ctypes.Structure):
@@ -69,6 +71,11 @@ class Batch(ctypes.Structure):
         ("transforms", ctypes.c_void_p),
         ("out_dtype", ctypes.c_int32),
         ("features_dtype", ctypes.c_int32),
+        ("radius_kind", ctypes.c_int32),
+        ("transform_flags", ctypes.c_int32),
+        ("rng_seed", ctypes.c_uint64),
+        ("rng_offset", ctypes.c_uint64),
+        ("random_translation", ctypes.c_double),
     ]
 
 
@@ -141,6 +148,8 @@ def lib():
         L.mvx_check_status.argtypes = [vp, vp]
         L.mvx_launches_per_call.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch)]
         L.mvx_voxelize_form.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch)]
+        L.mvx_random_transforms.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, vp, vp]
+        L.mvx_random_transforms.restype = ctypes.c_int
         L.mvx_profile_begin.argtypes = [ctypes.c_int]
         dp = ctypes.POINTER(ctypes.c_double)
         L.mvx_profile_end.argtypes = [dp, dp, dp, ctypes.POINTER(ctypes.c_int)]
@@ -155,7 +164,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "mvx_version", "mvx_last_error", "mvx_workspace_bytes", "mvx_host_staging_bytes", "mvx_voxelize",
     "mvx_voxelize_host", "mvx_check_status", "mvx_launches_per_call", "mvx_voxelize_form", "mvx_profile_begin",
-    "mvx_profile_end",
+    "mvx_profile_end", "mvx_random_transforms",
 ]
 
 

@@ -80,6 +80,10 @@ int check_args(const mvx_grid_spec* s, const mvx_batch* b) {
     if (b->mode != MVX_MODE_TYPES && b->out_channels != C) return fail(MVX_ERR_BAD_SHAPE, "Output grid dimension incorrect");
     if (b->out_dtype < MVX_OUT_F32 || b->out_dtype > MVX_OUT_F64) return fail(MVX_ERR_BAD_ENUM, "out_dtype");
     if (b->features_dtype != MVX_F32 && b->features_dtype != MVX_U8 && b->features_dtype != MVX_F16) return fail(MVX_ERR_BAD_ENUM, "features_dtype");
+    if (b->radius_kind < MVX_RADIUS_PYFLOAT || b->radius_kind > MVX_RADIUS_NP_F32) return fail(MVX_ERR_BAD_ENUM, "radius_kind");
+    if (b->transform_flags & ~(MVX_TF_ROTATE | MVX_TF_TRANSLATE | MVX_TF_TRANSLATE_ONCE)) return fail(MVX_ERR_BAD_ENUM, "transform_flags");
+    if ((b->transform_flags & MVX_TF_TRANSLATE) && !b->transforms && !(b->random_translation > 0.0))
+        return fail(MVX_ERR_BAD_SHAPE, "random_translation must be positive when the translation is drawn on the device");
     if (b->num_mols > 0 && !b->mol_offsets) return fail(MVX_ERR_NULL_POINTER, "mol_offsets");
     if (b->total_atoms > 0) {
         if (!b->coords) return fail(MVX_ERR_NULL_POINTER, "coords");
@@ -130,6 +134,15 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
         g.r_scalar32 = (float)b->radius;
         g.clip_lo = g.lower - b->radius;     // numpy/voxelizer.py:487
         g.clip_hi = g.upper + b->radius;     // :488
+        if (b->radius_kind == MVX_RADIUS_NP_F64) {
+            // np.float64 scalar: dr = fp64(dist32) / r64 <= 1.0 in fp64 (numpy/voxelizer.py:546-555), i.e. dist32 <= r64,
+            // i.e. dist32 <= the largest fp32 not above r64 — the kernels' fp32 radius is r64 rounded DOWN
+            if ((double)g.r_scalar32 > b->radius) g.r_scalar32 = std::nextafterf(g.r_scalar32, 0.f);
+        } else if (b->radius_kind == MVX_RADIUS_NP_F32) {
+            // np.float32 scalar: python-float bound -/+ np.float32 is fp32 arithmetic (NEP 50, :487-488)
+            g.clip_lo = (double)((float)g.lower - g.r_scalar32);
+            g.clip_hi = (double)((float)g.upper + g.r_scalar32);
+        }
         reach = std::fmax(b->radius, (double)g.r_scalar32);
     } else if (chan_feat) {
         // atom_size = radii.max() is an np.float32 scalar: the python-float bounds are demoted (NEP 50),
@@ -360,7 +373,9 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         pp.mol_offsets = batch->mol_offsets;
         pp.coords = batch->coords; pp.coords_f64 = batch->coords_dtype == MVX_F64;
         pp.centers = batch->centers; pp.centers_f64 = batch->centers_dtype == MVX_F64;
-        pp.types = batch->types; pp.radii = batch->radii; pp.transforms = batch->transforms;
+        pp.types = batch->types; pp.radii = batch->radii;
+        pp.tf_flags = batch->transform_flags; pp.transforms = batch->transform_flags ? batch->transforms : nullptr;
+        pp.rng_seed = batch->rng_seed; pp.rng_offset = batch->rng_offset; pp.rng_translation = batch->random_translation;
         pp.recs = recs; pp.colrange = colrange; pp.status = status;
         pp.alayers = layered(pl.form) ? (uint32_t*)(ws + pl.off_alayers) : nullptr;
         pp.kcnt = layered(pl.form) ? (uint32_t*)(ws + pl.off_kcnt) : nullptr;
@@ -377,6 +392,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         lp.B = B; lp.ncol = pl.ncol; lp.ncx = pl.geo.ncx; lp.maxcols = pl.maxcols; lp.zl = pl.zl; lp.nl = pl.nlayers;
         lp.nzc = pl.nzc; lp.tz = pl.tz; lp.dim = spec->dimension; lp.mode = batch->mode;
         lp.C = batch->mode == MVX_MODE_FEATURES ? C : 0; lp.es4 = pl.es4;
+        lp.feat_vec = (C % 4 == 0) && ((uintptr_t)batch->features % 16 == 0);
         lp.mol_offsets = batch->mol_offsets; lp.colrange = colrange; lp.alayers = (const uint32_t*)(ws + pl.off_alayers);
         lp.recs = recs; lp.types = batch->types; lp.features = (const float*)batch->features;
         lp.bins = bins; lp.lbins = (uint2*)(ws + pl.off_lbins);
@@ -477,6 +493,19 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
     return MVX_OK;
 }
 
+int mvx_random_transforms(uint64_t rng_seed, uint64_t rng_offset, int32_t num_mols, int32_t transform_flags,
+                          double random_translation, double* out, void* stream) {
+    if (num_mols < 0) return fail(MVX_ERR_BAD_SHAPE, "negative batch size");
+    if (num_mols == 0) return MVX_OK;
+    if (!out) return fail(MVX_ERR_NULL_POINTER, "out is NULL");
+    if (transform_flags & ~(MVX_TF_ROTATE | MVX_TF_TRANSLATE | MVX_TF_TRANSLATE_ONCE)) return fail(MVX_ERR_BAD_ENUM, "transform_flags");
+    mvx::DrawParams dp;
+    dp.seed = rng_seed; dp.offset = rng_offset; dp.B = num_mols; dp.flags = transform_flags; dp.rt = random_translation; dp.out = out;
+    mvx::mvx_draw_transforms_kernel<<<(unsigned)((num_mols + 127) / 128), 128, 0, (cudaStream_t)stream>>>(dp);
+    MVX_CUDA_OK(cudaGetLastError());
+    return MVX_OK;
+}
+
 int mvx_profile_begin(int max_calls) {
     if (g_prof.active) return fail(MVX_ERR_UNSUPPORTED, "a profile is already open on this thread");
     if (max_calls < 1) return fail(MVX_ERR_BAD_SHAPE, "max_calls must be >= 1");
@@ -552,7 +581,7 @@ void plan_staging(const mvx_grid_spec* s, const mvx_batch* b, Staging* sg) {
     sg->off_features = off; off += align_up(b->mode == MVX_MODE_FEATURES ? N * C * feature_bytes(b->features_dtype) : 0);
     size_t nr = s->radii_type == MVX_RADII_ATOM_WISE ? N : (s->radii_type == MVX_RADII_CHANNEL_WISE ? C : 0);
     sg->off_radii = off;    off += align_up(nr * sizeof(float));
-    sg->off_transforms = off; off += align_up(b->transforms ? B * 12 * sizeof(double) : 0);
+    sg->off_transforms = off; off += align_up((b->transforms && b->transform_flags) ? B * 7 * sizeof(double) : 0);
     sg->total = off;
 }
 }  // namespace
@@ -619,8 +648,8 @@ int mvx_voxelize_host(const mvx_grid_spec* spec, const mvx_batch* hb, void* out,
             db.radii = (const float*)(dv + sg.off_radii);
         }
     }
-    if (hb->transforms) {
-        MVX_CUDA_OK(put(sg.off_transforms, hb->transforms, B * 12 * sizeof(double)));
+    if (hb->transforms && hb->transform_flags) {
+        MVX_CUDA_OK(put(sg.off_transforms, hb->transforms, B * 7 * sizeof(double)));
         db.transforms = (const double*)(dv + sg.off_transforms);
     }
     if (pack != nullptr) MVX_CUDA_OK(cudaMemcpyAsync(dv, pack, sg.total, cudaMemcpyHostToDevice, st));

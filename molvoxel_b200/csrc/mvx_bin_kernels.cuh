@@ -2,6 +2,7 @@
 // (compiled into the API translation unit only; see mvx_common.cuh for the path map and data layout).
 #pragma once
 #include "mvx_common.cuh"
+#include "mvx_rigid.cuh"
 
 namespace mvx {
 
@@ -25,27 +26,37 @@ __global__ void __launch_bounds__(256) mvx_prep_kernel(const PrepParams P) {
     }
     const int mol = lo;
 
+    // centring in numpy's promoted dtype (fp32 - fp32 stays fp32, numpy/voxelizer.py:263), then the optional rigid
+    // transform in that same dtype (:265), then fp64 (:268)
     double p[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        if (P.centers == nullptr) {
-            p[k] = load_coord(P.coords, P.coords_f64, 3 * n + k);
-        } else if (!P.coords_f64 && !P.centers_f64) {   // fp32 - fp32 stays fp32 (numpy promotion)
-            float a = reinterpret_cast<const float*>(P.coords)[3 * n + k];
-            float b = reinterpret_cast<const float*>(P.centers)[3 * (int64_t)mol + k];
-            p[k] = (double)__fsub_rn(a, b);
+    const bool all_f32 = !P.coords_f64 && (P.centers == nullptr || !P.centers_f64);
+    Rigid R;
+    if (P.tf_flags != 0) {
+        if (P.transforms != nullptr) {
+            const double* T = P.transforms + 7 * (int64_t)mol;
+            R.q[0] = T[0]; R.q[1] = T[1]; R.q[2] = T[2]; R.q[3] = T[3];
+            R.t[0] = T[4]; R.t[1] = T[5]; R.t[2] = T[6];
         } else {
-            p[k] = __dsub_rn(load_coord(P.coords, P.coords_f64, 3 * n + k),
-                             load_coord(P.centers, P.centers_f64, 3 * (int64_t)mol + k));
+            draw_rigid(P.rng_seed, P.rng_offset + (unsigned long long)mol, P.tf_flags, P.rng_translation, R);
         }
     }
-
-    if (P.transforms != nullptr) {   // rigid augmentation about the centre: R.p + t (numpy/transform.py:43-60)
-        const double* T = P.transforms + 12 * (int64_t)mol;
-        const double q0 = T[0] * p[0] + T[1] * p[1] + T[2] * p[2] + T[9];
-        const double q1 = T[3] * p[0] + T[4] * p[1] + T[5] * p[2] + T[10];
-        const double q2 = T[6] * p[0] + T[7] * p[1] + T[8] * p[2] + T[11];
-        p[0] = q0; p[1] = q1; p[2] = q2;
+    if (all_f32) {
+        float pf[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            pf[k] = reinterpret_cast<const float*>(P.coords)[3 * n + k];
+            if (P.centers != nullptr) pf[k] = __fsub_rn(pf[k], reinterpret_cast<const float*>(P.centers)[3 * (int64_t)mol + k]);
+        }
+        if (P.tf_flags != 0) apply_rigid<float>(pf, R, P.tf_flags);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) p[k] = (double)pf[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            p[k] = load_coord(P.coords, P.coords_f64, 3 * n + k);
+            if (P.centers != nullptr) p[k] = __dsub_rn(p[k], load_coord(P.centers, P.centers_f64, 3 * (int64_t)mol + k));
+        }
+        if (P.tf_flags != 0) apply_rigid<double>(p, R, P.tf_flags);
     }
 
     bool keep = true;
@@ -377,6 +388,7 @@ struct LBinParams {
     double res, half_width, sigma;
     float tau_lin, tau_quad;
     int B, ncol, ncx, maxcols, zl, nl, nzc, tz, dim, mode, C, es4;
+    int feat_vec;   // feature rows can be read as float4 (C % 4 == 0 and a 16-byte aligned base)
     int64_t N;
     const int32_t* mol_offsets;
     const uint32_t* colrange;
@@ -539,7 +551,7 @@ __global__ void __launch_bounds__(256) mvx_lbuild_kernel(const LBinParams P) {
         return cm;
     };
     auto feature_word = [&](const float* f, const int k) -> float4 {   // word k of the padded feature row
-        if ((P.C & 3) == 0) return 4 * k < P.C ? __ldg(reinterpret_cast<const float4*>(f) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (P.feat_vec) return 4 * k < P.C ? __ldg(reinterpret_cast<const float4*>(f) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         float v[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) v[c] = (4 * k + c < P.C) ? __ldg(f + 4 * k + c) : 0.f;
@@ -628,6 +640,17 @@ __global__ void __launch_bounds__(256) mvx_lbuild_kernel(const LBinParams P) {
             for (int k = 0; k < ES4 - 3; ++k) e[3 + k] = feature_word(f, k);
         }
     }
+}
+
+// The transforms prep draws for molecules [offset, offset + B): same device function, one thread per molecule.
+__global__ void __launch_bounds__(128) mvx_draw_transforms_kernel(const DrawParams P) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= P.B) return;
+    Rigid R;
+    draw_rigid(P.seed, P.offset + (unsigned long long)m, P.flags, P.rt, R);
+    double* o = P.out + 7 * (size_t)m;
+    o[0] = R.q[0]; o[1] = R.q[1]; o[2] = R.q[2]; o[3] = R.q[3];
+    o[4] = R.t[0]; o[5] = R.t[1]; o[6] = R.t[2];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -66,7 +66,10 @@ struct PrepParams {
     const void* centers; int centers_f64;
     const int32_t* types;
     const float* radii;
-    const double* transforms;   // (B,12) or nullptr
+    const double* transforms;   // (B,7) explicit (quaternion, translation) per molecule, or nullptr = drawn here
+    int tf_flags;               // kTf* bits; 0 = no rigid transform
+    unsigned long long rng_seed, rng_offset;
+    double rng_translation;
     AtomRec* recs;
     uint32_t* colrange;
     int* status;

@@ -1,14 +1,24 @@
 """Random rigid transform (rotation about the centre + translation) applied before voxelization.
 
 Interface of reference molvoxel/voxelizer/base/transform.py:6-33 and numpy/transform.py:10-80
-(`RandomTransform.forward`, `get_transform() -> T`, `T(coords, center)`).  Random numbers come
-from numpy's global RNG in the reference's draw order (3 uniforms for the quaternion,
-numpy/_quaternion.py:13-21, then 3 for the translation, numpy/transform.py:74-76), so
-`np.random.seed(s)` reproduces the reference's transforms.  The rotation is applied as a 3x3
-matrix built from the unit quaternion.  Deliberate deviation: the numpy backend
-adds the translation twice when a rotation is also requested (numpy/transform.py:56-59); this
-backend applies it once, like the reference's torch backend (torch/transform.py:56-60).
-The numerics of this step are outside the parity metric (RNG-dependent).
+(`RandomTransform.forward`, `get_transform() -> T`, `T(coords, center)`, `T.create`).
+
+Two sources of randomness:
+
+* host draws from numpy's global RNG in the reference's order — `do_random_transform` draws the quaternion
+  first (3 uniforms, numpy/_quaternion.py:13-21) and then the translation (3 uniforms, numpy/transform.py:74-76);
+  `T.create` draws the translation first (numpy/transform.py:19-33) — so `np.random.seed(s)` reproduces the
+  reference's transforms exactly.  `Voxelizer(rng="numpy")` uses these and hands them to the kernels as
+  explicit (quaternion, translation) rows;
+* the device generator (`Voxelizer(rng="philox")`, the default): Philox4x32-10 keyed by (seed, molecule index),
+  drawn inside the per-atom prep kernel (csrc/mvx_rigid.cuh) — no host work per molecule.
+
+Either way the transform itself is applied by the prep kernel with the reference's arithmetic, operation for
+operation: the two quaternion products of numpy/_quaternion.py:28-54 and then the translation, added TWICE when
+a rotation is also requested (numpy/transform.py:56-59 — numpy and numba backends) unless
+`translate_once=True` asks for the torch backend's behaviour (torch/transform.py:56-60).  `do_transform` below is
+the same arithmetic on the host (numpy arrays or torch tensors) for callers that use `T` / `RandomTransform`
+directly, as the reference's tests do (test/test_run_numpy.py:34-40).
 """
 from __future__ import annotations
 
@@ -17,99 +27,93 @@ import math
 import numpy as np
 import torch
 
+PI2 = 2 * math.pi
 
-def random_unit_quaternion():
+
+def random_quaternion():
+    """Uniform random rotation as a unit quaternion from three uniforms (numpy/_quaternion.py:13-21)."""
     u1, u2, u3 = np.random.rand(3)
-    a, b = math.sqrt(1.0 - u1), math.sqrt(u1)
-    return (a * math.sin(2 * math.pi * u2), a * math.cos(2 * math.pi * u2),
-            b * math.sin(2 * math.pi * u3), b * math.cos(2 * math.pi * u3))
+    lo, hi = math.sqrt(1 - u1), math.sqrt(u1)
+    return (lo * math.sin(PI2 * u2), lo * math.cos(PI2 * u2), hi * math.sin(PI2 * u3), hi * math.cos(PI2 * u3))
 
 
-def quaternion_to_matrix(q) -> np.ndarray:
-    """Rotation matrix of v -> q v q^-1 for a unit quaternion q = (w, x, y, z)."""
-    w, x, y, z = q
-    return np.array([
-        [1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
-        [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
-        [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)],
-    ], dtype=np.float64)
+def random_translation_vector(random_translation: float):
+    """(1, 3) float32, each component ~ U(-t, t) (numpy/transform.py:26, :76)."""
+    return np.random.uniform(-random_translation, random_translation, size=(1, 3)).astype(np.float32)
 
 
-def _draw(random_translation, random_rotation):
-    rot = quaternion_to_matrix(random_unit_quaternion()) if random_rotation else None
-    if random_translation is not None and random_translation > 0.0:
-        tr = np.random.uniform(-random_translation, random_translation, size=(1, 3)).astype(np.float32).astype(np.float64)
-    else:
-        tr = None
-    return rot, tr
-
-
-def random_transform_params(num_mols, random_translation, random_rotation):
-    """One (rotation | None, translation | None) pair per molecule."""
-    return [_draw(random_translation, random_rotation) for _ in range(num_mols)]
-
-
-def transform_matrix_array(params) -> np.ndarray:
-    """(B, 12) float64 for the C ABI: row-major rotation (identity if None) followed by the translation."""
-    out = np.zeros((len(params), 12), dtype=np.float64)
-    for m, (rot, tr) in enumerate(params):
-        out[m, :9] = (np.eye(3) if rot is None else rot).reshape(-1)
-        if tr is not None:
-            out[m, 9:] = np.asarray(tr, dtype=np.float64).reshape(-1)
-    return out
-
-
-def _apply_one(xyz, center, rot, tr):
+def rotate(xyz, quaternion):
+    """q (0, p) q^-1 with the reference's operation order (numpy/_quaternion.py:28-54); xyz is (V, 3), numpy or torch.
+    Python-float quaternion components are weak scalars, so the arithmetic runs in xyz's dtype like the reference's."""
+    q0, q1, q2, q3 = quaternion
+    x, y, z = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    o = x * 0
+    a0 = q0 * o - q1 * x - q2 * y - q3 * z
+    a1 = q0 * x + q1 * o + q2 * z - q3 * y
+    a2 = q0 * y - q1 * z + q2 * o + q3 * x
+    a3 = q0 * z + q1 * y - q2 * x + q3 * o
+    b0, b1, b2, b3 = q0, q1 * -1, q2 * -1, q3 * -1
+    rx = a0 * b1 + a1 * b0 + a2 * b3 - a3 * b2
+    ry = a0 * b2 - a1 * b3 + a2 * b0 + a3 * b1
+    rz = a0 * b3 + a1 * b2 - a2 * b1 + a3 * b0
     lib = torch if isinstance(xyz, torch.Tensor) else np
-    if isinstance(xyz, torch.Tensor):
-        conv = lambda a: torch.as_tensor(a, dtype=xyz.dtype, device=xyz.device)   # noqa: E731
-    else:
-        conv = lambda a: np.asarray(a, dtype=xyz.dtype)   # noqa: E731
-    if rot is not None:
-        if center is not None:
-            xyz = lib.matmul(xyz - center, conv(rot).T) + center
-        else:
-            xyz = lib.matmul(xyz, conv(rot).T)
-    if tr is not None:
-        xyz = xyz + conv(tr)
-    return xyz
+    return lib.stack([rx, ry, rz], -1)
 
 
-def apply_transform(coords, mol_offsets, centers, params):
-    """Centre each molecule, rotate about the origin, translate.  Returns (coords', None): the result
-    is already centred, like the reference which transforms after subtracting the centre."""
+def do_transform(coords, center=None, translation=None, quaternion=None, translate_once: bool = False):
+    """numpy/transform.py:43-60 on the host: rotation about `center`, then the translation — twice when rotating
+    (the numpy backend's behaviour) unless translate_once."""
     is_t = isinstance(coords, torch.Tensor)
-    x = coords.to(torch.float64) if is_t else np.asarray(coords, dtype=np.float64)
-    offs = mol_offsets.tolist() if hasattr(mol_offsets, "tolist") else list(mol_offsets)
-    parts = []
-    for m, (rot, tr) in enumerate(params):
-        seg = x[offs[m]:offs[m + 1]]
-        if centers is not None:
-            c = centers[m].reshape(1, 3)
-            c = (c.to(x.device, torch.float64) if isinstance(c, torch.Tensor) else torch.as_tensor(np.asarray(c, dtype=np.float64), device=x.device)) if is_t \
-                else np.asarray(c.detach().cpu().numpy() if isinstance(c, torch.Tensor) else c, dtype=np.float64)
-            seg = seg - c
-        parts.append(_apply_one(seg, None, rot, tr))
-    out = (torch.cat(parts, 0) if is_t else np.concatenate(parts, 0)) if parts else x
-    return out, None
+    if translation is not None and is_t:
+        translation = torch.as_tensor(np.asarray(translation), device=coords.device)
+    if quaternion is not None:
+        if center is not None:
+            center = center.reshape(1, 3)
+            coords = rotate(coords - center, quaternion) + center
+        else:
+            coords = rotate(coords, quaternion)
+        if translation is not None and not translate_once:
+            coords = coords + translation
+    if translation is not None:
+        coords = coords + translation
+    return coords
+
+
+def do_random_transform(coords, center=None, random_translation=0.0, random_rotation=False, translate_once: bool = False):
+    """numpy/transform.py:63-80: quaternion drawn first, then the translation."""
+    quaternion = random_quaternion() if random_rotation else None
+    translation = None
+    if random_translation is not None and random_translation > 0.0:
+        translation = random_translation_vector(random_translation)
+    return do_transform(coords, center, translation, quaternion, translate_once)
 
 
 class T:
-    """A frozen transform (numpy/transform.py:10-33): reusable across calls."""
+    """A frozen transform (numpy/transform.py:10-33): reusable across calls and voxelizers."""
 
-    def __init__(self, translation, rotation):
+    translate_once = False
+
+    def __init__(self, translation, quaternion):
         self.translation = translation
-        self.rotation = rotation
+        self.quaternion = quaternion
 
     def __call__(self, coords, center):
-        if isinstance(center, torch.Tensor) or isinstance(center, np.ndarray):
-            center = center.reshape(1, 3)
-        return _apply_one(coords, center, self.rotation, self.translation)
+        return do_transform(coords, center, self.translation, self.quaternion, self.translate_once)
 
     @classmethod
     def create(cls, random_translation: float = 0.0, random_rotation: bool = False):
-        rot, tr = _draw(random_translation, random_rotation)
-        return cls(tr, rot)
+        # the reference draws the translation FIRST here (numpy/transform.py:19-33), unlike do_random_transform
+        translation = random_translation_vector(random_translation) if random_translation > 0.0 else None
+        quaternion = random_quaternion() if random_rotation else None
+        return cls(translation, quaternion)
+
+    def as_row(self) -> np.ndarray:
+        """(7,) float64 for the C ABI (mvx_batch.transforms): quaternion (identity if None), translation (0 if None)."""
+        row = np.zeros(7, dtype=np.float64)
+        row[:4] = (1.0, 0.0, 0.0, 0.0) if self.quaternion is None else self.quaternion
+        if self.translation is not None:
+            row[4:] = np.asarray(self.translation, dtype=np.float64).reshape(3)
+        return row
 
 
 class RandomTransform:
@@ -120,9 +124,35 @@ class RandomTransform:
         self.random_rotation = random_rotation
 
     def forward(self, coords, center):
-        return self.get_transform()(coords, center)
+        return do_random_transform(coords, center, self.random_translation, self.random_rotation, self.class_T.translate_once)
 
     __call__ = forward
 
     def get_transform(self) -> T:
         return self.class_T.create(self.random_translation, self.random_rotation)
+
+
+def host_transform_rows(num_mols: int, random_translation, random_rotation) -> np.ndarray:
+    """(B, 7) float64 rows drawn from numpy's global RNG exactly as B consecutive reference forward_* calls would
+    (quaternion first, then translation: numpy/transform.py:63-80)."""
+    rows = np.zeros((num_mols, 7), dtype=np.float64)
+    rows[:, 0] = 1.0   # identity quaternion (scalar part first)
+    translate = random_translation is not None and random_translation > 0.0
+    for m in range(num_mols):
+        if random_rotation:
+            rows[m, :4] = random_quaternion()
+        if translate:
+            rows[m, 4:] = random_translation_vector(random_translation).reshape(3)
+    return rows
+
+
+def transform_rows(transforms, num_mols: int) -> np.ndarray:
+    """Explicit per-molecule transforms for the C ABI: a (B, 7) array, one T for all molecules, or a sequence of T."""
+    if isinstance(transforms, T):
+        return np.tile(transforms.as_row(), (num_mols, 1))
+    if isinstance(transforms, (list, tuple)) and len(transforms) > 0 and isinstance(transforms[0], T):
+        assert len(transforms) == num_mols, f"one transform per molecule: {len(transforms)} vs {num_mols}"
+        return np.stack([t.as_row() for t in transforms])
+    rows = np.ascontiguousarray(np.asarray(transforms, dtype=np.float64))
+    assert rows.shape == (num_mols, 7), f"transforms should be (B, 7): {rows.shape} vs {(num_mols, 7)}"
+    return rows

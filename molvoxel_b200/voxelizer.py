@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .transform import RandomTransform, random_transform_params, transform_matrix_array
+from .transform import RandomTransform, host_transform_rows, transform_rows
 
 
 def _norm(x):
@@ -76,8 +76,21 @@ class Voxelizer:
         assert out_dtype in (torch.float32, torch.bfloat16, torch.float16, torch.float64), \
             "out_dtype must be float32, bfloat16, float16 or float64"
         self.out_dtype = out_dtype
+        # random rigid transform (random_translation / random_rotation of every forward_*): where the per-molecule
+        # parameters come from.  "philox" (default): drawn on the device inside the prep kernel from a counter-based
+        # generator keyed by (seed, molecule index) — molecule indices continue across calls, `rng_offset=` pins them
+        # for sharded sweeps.  "numpy": drawn on the host from numpy's global RNG in the reference's order, so
+        # np.random.seed(s) reproduces the reference's augmentation bit for bit (a Python loop per molecule: slow).
+        self.rng = kwargs.get("rng", "philox")
+        assert self.rng in ("philox", "numpy"), "rng must be 'philox' or 'numpy'"
+        self._seed = int(kwargs.get("seed", 0)) & 0xFFFFFFFFFFFFFFFF
+        self._mol_counter = 0
+        # the numpy / numba backends add the translation twice when a rotation is also requested
+        # (numpy/transform.py:56-59); translate_once=True gives the torch backend's single addition
+        self.translate_once = bool(kwargs.get("translate_once", False))
         self._ws = None
         self._pipe = None
+        self._sticky_flags = 0
         _lib.lib()   # fail loudly here if the CUDA library cannot be built/loaded
 
     # ---- properties of the reference contract (base/voxelizer.py:40-97) ----
@@ -236,24 +249,59 @@ class Voxelizer:
     # ---- batched driver (new, additive; per-molecule semantics = B independent reference calls) ----
     def forward_types_batch(self, coords, mol_offsets, centers, types, radii, num_channels,
                             random_translation: float = 0.0, random_rotation: bool = False, out=None,
-                            non_blocking: bool = False):
+                            non_blocking: bool = False, max_radius=None, transforms=None, rng_offset=None):
         """CSR batch -> (B, C, D, H, W).  non_blocking=True with HOST inputs pipelines the H2D copies of this
-        call behind the kernels of the previous one (pinned inputs; call check_status() to synchronise)."""
+        call behind the kernels of the previous one (pinned inputs; call check_status() to synchronise).
+        max_radius: a host-known bound of an array `radii` (saves a device->host read on the device path).
+        transforms: explicit rigid transforms ((B, 7) rows, a T, or a list of T) instead of random draws.
+        rng_offset: global index of the batch's first molecule for the device generator (sharded / chunked sweeps)."""
         return self._forward_batch("types", coords, mol_offsets, centers, types, radii, int(num_channels),
-                                   random_translation, random_rotation, out, non_blocking=non_blocking)
+                                   random_translation, random_rotation, out, non_blocking=non_blocking,
+                                   max_radius=max_radius, transforms=transforms, rng_offset=rng_offset)
 
     def forward_features_batch(self, coords, mol_offsets, centers, features, radii,
                                random_translation: float = 0.0, random_rotation: bool = False, out=None,
-                               non_blocking: bool = False):
+                               non_blocking: bool = False, max_radius=None, transforms=None, rng_offset=None):
         return self._forward_batch("features", coords, mol_offsets, centers, features, radii,
                                    int(features.shape[1]), random_translation, random_rotation, out,
-                                   non_blocking=non_blocking)
+                                   non_blocking=non_blocking, max_radius=max_radius, transforms=transforms,
+                                   rng_offset=rng_offset)
 
     def forward_single_batch(self, coords, mol_offsets, centers, radii,
                              random_translation: float = 0.0, random_rotation: bool = False, out=None,
-                             non_blocking: bool = False):
+                             non_blocking: bool = False, max_radius=None, transforms=None, rng_offset=None):
         return self._forward_batch("single", coords, mol_offsets, centers, None, radii, 1,
-                                   random_translation, random_rotation, out, non_blocking=non_blocking)
+                                   random_translation, random_rotation, out, non_blocking=non_blocking,
+                                   max_radius=max_radius, transforms=transforms, rng_offset=rng_offset)
+
+    def seed(self, seed: int, first_molecule: int = 0):
+        """Key of the device generator and the molecule index the next call starts at."""
+        self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._mol_counter = int(first_molecule)
+
+    def random_transforms(self, num_mols: int, random_translation: float = 0.0, random_rotation: bool = False,
+                          rng_offset: int = 0) -> torch.Tensor:
+        """The (B, 7) rows (quaternion, translation) the device generator gives molecules
+        [rng_offset, rng_offset + num_mols) under the current seed — what a forward_* call with the same arguments
+        applies.  Passing them back as `transforms=` gives bit-identical grids."""
+        flags = self._transform_flags(random_translation, random_rotation)
+        out = torch.zeros((num_mols, 7), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.raise_for_status(_lib.lib().mvx_random_transforms(
+                ctypes.c_uint64(self._seed), ctypes.c_uint64(int(rng_offset)), int(num_mols), flags,
+                float(random_translation or 0.0), ctypes.c_void_p(out.data_ptr()), stream))
+        return out
+
+    def _transform_flags(self, random_translation, random_rotation) -> int:
+        flags = 0
+        if random_rotation:
+            flags |= _lib.TF_ROTATE
+        if random_translation is not None and random_translation > 0.0:
+            flags |= _lib.TF_TRANSLATE
+        if flags and self.translate_once:
+            flags |= _lib.TF_TRANSLATE_ONCE
+        return flags
 
     # ---- implementation ----
     def _spec(self):
@@ -292,6 +340,9 @@ class Voxelizer:
         slot["index"] = pipe["idx"]
         pipe["idx"] ^= 1
         slot["done"].synchronize()
+        # the status word of the call that last used this slot has landed: keep its flags (sticky until check_status)
+        self._sticky_flags |= int(pipe["status"][slot["index"]])
+        pipe["status"][slot["index"]] = 0
         cur = torch.cuda.current_stream(self.device)
         outs = []
         with torch.cuda.stream(pipe["copy"]):
@@ -312,7 +363,8 @@ class Voxelizer:
         return outs, slot
 
     def _forward_batch(self, mode, coords, mol_offsets, centers, channels, radii, C, random_translation,
-                       random_rotation, out, infer_types_channels=False, max_radius=None, non_blocking=False):
+                       random_rotation, out, infer_types_channels=False, max_radius=None, non_blocking=False,
+                       transforms=None, rng_offset=None):
         have_cuda = self.device.type == "cuda" and torch.cuda.is_available()
         coords, centers, channels, radii = _norm(coords), _norm(centers), _norm(channels), _norm(radii)
         on_device = isinstance(coords, torch.Tensor) and coords.is_cuda
@@ -326,7 +378,8 @@ class Voxelizer:
                 ("coords", coords), ("offs", np.asarray(mol_offsets, dtype=np.int32) if not isinstance(mol_offsets, torch.Tensor) else mol_offsets),
                 ("centers", centers), ("chan", channels), ("radii", None if _is_scalar(radii) else radii)])
             res = self._forward_batch(mode, coords_d, offs_d, centers_d, chan_d, radii if _is_scalar(radii) else radii_d, C,
-                                      random_translation, random_rotation, out, False, max_radius)
+                                      random_translation, random_rotation, out, False, max_radius,
+                                      transforms=transforms, rng_offset=rng_offset)
             cur = torch.cuda.current_stream(self.device)
             ws_ptr_off = (-self._ws.data_ptr()) % 256
             self._pipe["status"][slot["index"]:slot["index"] + 1].copy_(
@@ -385,11 +438,26 @@ class Voxelizer:
         if out is None:
             out = torch.empty((B, out_channels, D, D, D), dtype=self.out_dtype, device=self.device)
 
-        # centring stays inside the kernel (fp64 or numpy's fp32-fp32 promotion); the optional random
-        # rigid transform is applied to centred coordinates first, like the reference (numpy/voxelizer.py:263-265)
-        transforms = None
-        if (random_translation is not None and random_translation > 0.0) or random_rotation:
-            transforms = transform_matrix_array(random_transform_params(B, random_translation, random_rotation))
+        # centring and the optional rigid transform stay inside the prep kernel, in numpy's promoted dtype
+        # (numpy/voxelizer.py:263-265).  Explicit transforms, or parameters drawn on the host in the reference's
+        # order (rng="numpy"), travel as (B, 7) rows; otherwise the device generator draws them.
+        tf_flags = 0
+        tf_rows = None
+        if transforms is not None:
+            tf_rows = transform_rows(transforms, B)
+            # which parts of the rows apply: the call's random_* arguments if any is set, else both
+            tf_flags = self._transform_flags(random_translation, random_rotation) or \
+                (_lib.TF_ROTATE | _lib.TF_TRANSLATE | (_lib.TF_TRANSLATE_ONCE if self.translate_once else 0))
+            if isinstance(transforms, RandomTransform.class_T) or (isinstance(transforms, (list, tuple)) and len(transforms) > 0):
+                ts = [transforms] if isinstance(transforms, RandomTransform.class_T) else list(transforms)
+                if all(t.quaternion is None for t in ts):   # translation only: one addition (numpy/transform.py:58-59)
+                    tf_flags &= ~_lib.TF_ROTATE
+                if all(t.translation is None for t in ts):
+                    tf_flags &= ~_lib.TF_TRANSLATE
+        else:
+            tf_flags = self._transform_flags(random_translation, random_rotation)
+            if tf_flags and self.rng == "numpy":
+                tf_rows = host_transform_rows(B, random_translation, random_rotation)
 
         keep = []   # keeps converted arrays alive until the call returns
 
@@ -408,6 +476,17 @@ class Voxelizer:
         b.num_channels, b.out_channels = C, out_channels
         b.radius, b.max_radius = 0.0, 0.0
         b.out_dtype = _lib.OUT_DTYPE[str(self.out_dtype).replace("torch.", "")]
+        b.transform_flags = tf_flags
+        if tf_flags and tf_rows is None:   # device-drawn: key + global molecule index
+            b.rng_seed = self._seed
+            b.random_translation = float(random_translation or 0.0)
+            if rng_offset is None:
+                rng_offset = self._mol_counter
+                self._mol_counter += B
+            b.rng_offset = int(rng_offset)
+        if self.is_radii_type_scalar:   # numpy's promotion depends on how the scalar is typed (NEP 50)
+            b.radius_kind = (_lib.RADIUS_NP_F64 if isinstance(radii, np.float64) else
+                             _lib.RADIUS_NP_F32 if isinstance(radii, np.float32) else _lib.RADIUS_PYFLOAT)
 
         def fdtype_of(x):
             if isinstance(x, torch.Tensor):
@@ -438,8 +517,8 @@ class Voxelizer:
                 r = dev(torch.as_tensor(radii), torch.float32)
                 b.radii = ptr(r)
                 b.max_radius = float(max_radius) if max_radius is not None else (float(r.max()) if r.numel() else 1.0)
-            if transforms is not None:
-                b.transforms = ptr(dev(torch.from_numpy(transforms), torch.float64))
+            if tf_rows is not None:
+                b.transforms = ptr(dev(torch.from_numpy(tf_rows), torch.float64))
         else:
             ptr = lambda a: ctypes.c_void_p(a.ctypes.data)   # noqa: E731
             b.mol_offsets = ptr(host(mol_offsets, np.int32))
@@ -465,8 +544,8 @@ class Voxelizer:
                 r = host(radii, np.float32)
                 b.radii = ptr(r)
                 b.max_radius = float(max_radius) if max_radius is not None else (float(r.max()) if r.size else 1.0)
-            if transforms is not None:
-                b.transforms = ptr(host(transforms, np.float64))
+            if tf_rows is not None:
+                b.transforms = ptr(host(tf_rows, np.float64))
 
         L = _lib.lib()
         spec = self._spec()
@@ -500,9 +579,10 @@ class Voxelizer:
         with torch.cuda.device(self.device):
             stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             _lib.raise_for_status(_lib.lib().mvx_check_status(ctypes.c_void_p(ws_ptr), stream))
-        if self._pipe is not None:   # status words copied back by the pipelined (non_blocking) calls
-            flags = int(self._pipe["status"][0]) | int(self._pipe["status"][1])
+        if self._pipe is not None:   # status words copied back by the pipelined (non_blocking) calls: sticky
+            flags = self._sticky_flags | int(self._pipe["status"][0]) | int(self._pipe["status"][1])
             self._pipe["status"].zero_()
+            self._sticky_flags = 0
             if flags & 1:
                 raise ValueError("a type index is outside [0, num_channels)")
             if flags & 2:

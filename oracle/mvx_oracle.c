@@ -61,6 +61,23 @@ static inline float pair_term(double px, double py, double pz, double gx, double
     return e;
 }
 
+/* The term when the scalar radius is an np.float64 (a strongly typed scalar under NEP 50): np.divide(dist32, r64)
+ * promotes to fp64 (:548), so the cutoff compares in fp64 (:555, :559) and the Gaussian is evaluated in fp64 (:558,
+ * sigma a python float); the caller narrows on accumulation (out32 += res64, :365/:476) or after the fp64 matmul (:226-235). */
+static inline double pair_term_r64(double px, double py, double pz, double gx, double gy, double gz,
+                                   double r64, double sigma, int binary) {
+    double dx = px - gx, dy = py - gy, dz = pz - gz;
+    double xx = dx * dx, yy = dy * dy, zz = dz * dz;
+    double s = (xx + yy) + zz;
+    float d32 = (float)sqrt(s);         /* dist.astype(float32), :545 */
+    double dr = (double)d32 / r64;      /* fp32 / np.float64 -> fp64, :548 */
+    if (binary) return (dr <= 1.0) ? 1.0 : 0.0;
+    double q = dr / sigma;
+    double e = exp(-0.5 * (q * q));
+    if (dr > 1.0) e = 0.0;
+    return e;
+}
+
 /* The same term with precision=64 (numpy/voxelizer.py:34): dist stays fp64 (:545 is a no-op), dr = dist / radii in fp64
  * (:548), np.exp(-0.5 * (dr / sigma) ** 2) in fp64 (:558), cutoff dr > 1.0 (:559) / dr <= 1.0 (:555). */
 static inline double pair_term64(double px, double py, double pz, double gx, double gy, double gz,
@@ -86,7 +103,9 @@ static inline double pair_term64(double px, double py, double pz, double gx, dou
  */
 static int mvxo_forward_p(const mvxo_spec *s, int mode, int V, const void *coords, int coords_f64,
                           const void *center, int center_f64, const int32_t *types, const float *features,
-                          int C, double radius, const float *radii, void *out_v, int out_channels, int prec64) {
+                          int C, double radius, const float *radii, void *out_v, int out_channels, int prec64,
+                          int radius_kind) {   /* scalar radius: 0 python float, 1 np.float64, 2 np.float32 */
+    const int radius_f64 = radius_kind == 1;
     float *out = (float *)out_v;      /* precision=32 (the default oracle) */
     double *out64 = (double *)out_v;  /* precision=64: get_empty_grid dtype :60-70, features/radii astype(fp64) :127-130 */
     const int D = s->dimension;
@@ -106,6 +125,13 @@ static int mvxo_forward_p(const mvxo_spec *s, int mode, int V, const void *coord
     /* out init: types/single zero (:279-281, :402-404); features writes every voxel (:158-160,:232-235). */
     memset(out_v, 0, (prec64 ? sizeof(double) : sizeof(float)) * plane * (size_t)out_channels);
     if (V == 0) return 0;
+    /* np.float64 scalar radius, precision=32: features go through an fp64 matmul that is narrowed once (:226-235) */
+    const int r64 = radius_f64 && !prec64 && s->radii_mode == MVXO_RADII_SCALAR;
+    double *acc64 = NULL;
+    if (r64 && mode == MVXO_MODE_FEATURES) {
+        acc64 = (double *)calloc(plane * (size_t)out_channels, sizeof(double));
+        if (!acc64) return -3;
+    }
 
     double *p = (double *)malloc(sizeof(double) * 3 * (size_t)V);
     float *rr = (float *)malloc(sizeof(float) * (size_t)V);   /* per-atom kernel radius */
@@ -144,6 +170,9 @@ static int mvxo_forward_p(const mvxo_spec *s, int mode, int V, const void *coord
         size_scalar = (double)m;
         thr_f32 = !prec64;   /* precision=64: radii.astype(float64).max() is np.float64, the bounds stay fp64 (:130, :138) */
     }
+    /* an np.float32 SCALAR radius: python-float bound -/+ np.float32 is fp32 arithmetic as well (:487-488, NEP 50);
+     * the block bounds are np.float64 array elements, so the cull stays fp64 (:504-511) */
+    if (s->radii_mode == MVXO_RADII_SCALAR && radius_kind == 2) thr_f32 = 1;
     for (int n = 0; n < V; ++n) {
         if (s->radii_mode == MVXO_RADII_SCALAR) rr[n] = (float)radius;
         else if (s->radii_mode == MVXO_RADII_ATOM) rr[n] = radii[n];
@@ -243,6 +272,18 @@ static int mvxo_forward_p(const mvxo_spec *s, int mode, int V, const void *coord
                             }
                             continue;
                         }
+                        if (r64) {
+                            double t = pair_term_r64(px, py, pz, gx, gy, gz, radius, s->sigma, s->binary);
+                            if (mode == MVXO_MODE_TYPES) {
+                                float *o = &out[(size_t)types[n] * plane + vox];
+                                *o = (float)((double)*o + t);                    /* fp32 += fp64: fp64 add, narrowed (:365) */
+                            } else if (mode == MVXO_MODE_SINGLE) {
+                                out[vox] = (float)((double)out[vox] + t);        /* :476 */
+                            } else if (t != 0.0) {
+                                for (int c = 0; c < C; ++c) acc64[(size_t)c * plane + vox] += (double)features[(size_t)n * C + c] * t;
+                            }
+                            continue;
+                        }
                         if (mode == MVXO_MODE_TYPES) {
                             float t = pair_term(px, py, pz, gx, gy, gz, rr[n], sigma32, s->binary);
                             out[(size_t)types[n] * plane + vox] += t;            /* :365 */
@@ -271,6 +312,10 @@ static int mvxo_forward_p(const mvxo_spec *s, int mode, int V, const void *coord
             }
         }
     }
+    if (acc64) {
+        for (size_t i = 0; i < plane * (size_t)out_channels; ++i) out[i] = (float)acc64[i];
+        free(acc64);
+    }
     free(p); free(rr); free(keep); free(blist); free(bounds);
     return 0;
 }
@@ -279,7 +324,7 @@ int mvxo_forward(const mvxo_spec *s, int mode, int V, const void *coords, int co
                  const void *center, int center_f64, const int32_t *types, const float *features,
                  int C, double radius, const float *radii, float *out, int out_channels) {
     return mvxo_forward_p(s, mode, V, coords, coords_f64, center, center_f64, types, features, C, radius, radii, out,
-                          out_channels, 0);
+                          out_channels, 0, 0);
 }
 
 /* precision=64 variant: out is (out_channels, D, D, D) float64. */
@@ -287,7 +332,7 @@ int mvxo_forward64(const mvxo_spec *s, int mode, int V, const void *coords, int 
                    const void *center, int center_f64, const int32_t *types, const float *features,
                    int C, double radius, const float *radii, double *out, int out_channels) {
     return mvxo_forward_p(s, mode, V, coords, coords_f64, center, center_f64, types, features, C, radius, radii, out,
-                          out_channels, 1);
+                          out_channels, 1, 0);
 }
 
 /*
@@ -300,7 +345,7 @@ typedef struct {
     const mvxo_spec *s; int mode; int B; const int32_t *mol_offsets; const void *coords; int coords_f64;
     const void *centers; int centers_f64; const int32_t *types; const float *features; int C;
     double radius; const float *radii; float *out; int out_channels;
-    int next; int rc; pthread_mutex_t mu;
+    int next; int rc; pthread_mutex_t mu; int radius_kind;
 } mvxo_job;
 
 static void *mvxo_worker(void *arg) {
@@ -319,21 +364,23 @@ static void *mvxo_worker(void *arg) {
         const void *zb = j->centers ? (const void *)((const char *)j->centers + zsz * 3 * (size_t)b) : NULL;
         const float *rb = j->radii;
         if (j->radii && s->radii_mode == MVXO_RADII_ATOM) rb = j->radii + a0;
-        int rc = mvxo_forward(s, j->mode, V, cb, j->coords_f64, zb, j->centers_f64,
-                              j->types ? j->types + a0 : NULL,
-                              j->features ? j->features + (size_t)a0 * j->C : NULL, j->C, j->radius, rb,
-                              j->out + per_mol * (size_t)b, j->out_channels);
+        int rc = mvxo_forward_p(s, j->mode, V, cb, j->coords_f64, zb, j->centers_f64,
+                                j->types ? j->types + a0 : NULL,
+                                j->features ? j->features + (size_t)a0 * j->C : NULL, j->C, j->radius, rb,
+                                j->out + per_mol * (size_t)b, j->out_channels, 0, j->radius_kind);
         if (rc != 0) { pthread_mutex_lock(&j->mu); j->rc = rc; pthread_mutex_unlock(&j->mu); }
     }
     return NULL;
 }
 
+/* radius_kind: 0 the scalar radius is a python float; 1 an np.float64 (numpy then divides in fp64, :546-548);
+ * 2 an np.float32 (fp32 clip bounds, :487-488). */
 int mvxo_forward_batch(const mvxo_spec *s, int mode, int B, const int32_t *mol_offsets, const void *coords,
                        int coords_f64, const void *centers, int centers_f64, const int32_t *types,
                        const float *features, int C, double radius, const float *radii, float *out,
-                       int out_channels, int num_threads) {
+                       int out_channels, int num_threads, int radius_kind) {
     mvxo_job j = {s, mode, B, mol_offsets, coords, coords_f64, centers, centers_f64, types, features, C,
-                  radius, radii, out, out_channels, 0, 0, PTHREAD_MUTEX_INITIALIZER};
+                  radius, radii, out, out_channels, 0, 0, PTHREAD_MUTEX_INITIALIZER, radius_kind};
     if (num_threads < 1) num_threads = 1;
     if (num_threads > 256) num_threads = 256;
     if (num_threads > B) num_threads = B > 0 ? B : 1;

@@ -78,6 +78,9 @@ def oracle_forward_batch(resolution, dimension, radii_type, density_type, sigma,
         features = np.ascontiguousarray(features, dtype=np.float32)
     radius = 0.0
     radii_arr = None
+    # an np.float64 scalar is strongly typed (NEP 50): the reference divides in fp64 (numpy/voxelizer.py:546-548);
+    # np.float32 / np.float16 scalars and python floats give fp32 arithmetic
+    radius_kind = 1 if isinstance(radii, np.float64) else (2 if isinstance(radii, np.float32) else 0)
     if np.isscalar(radii):
         radius = float(radii)
     else:
@@ -105,7 +108,7 @@ def oracle_forward_batch(resolution, dimension, radii_type, density_type, sigma,
     rc = lib.mvxo_forward_batch(
         ctypes.byref(spec), _MODE[mode], B, _ptr(mol_offsets), _ptr(coords), int(coords.dtype == np.float64),
         _ptr(centers), int(centers is not None and centers.dtype == np.float64), _ptr(types), _ptr(features),
-        C, ctypes.c_double(radius), _ptr(radii_arr), _ptr(out), oc, int(num_threads))
+        C, ctypes.c_double(radius), _ptr(radii_arr), _ptr(out), oc, int(num_threads), radius_kind)
     if rc != 0:
         raise AssertionError(f"oracle rejected the arguments (code {rc})")
     return out

@@ -24,6 +24,10 @@ class GoldenCase:
         self.channels = z["channels"] if "channels" in z.files else None
         r = z["radii"]
         self.radii = float(r) if r.ndim == 0 else r
+        if r.ndim == 0 and self.cfg.get("radius_f64"):     # an np.float64 scalar radius: fp64 division in the reference
+            self.radii = np.float64(r)
+        elif r.ndim == 0 and self.cfg.get("radius_f32"):
+            self.radii = np.float32(r)
         self.shape = tuple(int(v) for v in z["shape"])
         self.sampled = "sample_idx" in z.files
         if self.sampled:
@@ -48,7 +52,7 @@ class GoldenCase:
             ref = self.sample_val
             peak = max(1.0, float(np.abs(ref).max()))
             err = float(np.abs(flat[self.sample_idx] - ref).max())
-            assert err <= gauss_tol * 8 * peak, f"{self.name}: sampled max-abs {err}"
+            assert err <= gauss_tol * peak, f"{self.name}: sampled max-abs {err}"
             nnz = (got.reshape(got.shape[0], -1) != 0).sum(1)
             assert np.array_equal(nnz, self.chan_nnz), f"{self.name}: per-channel nnz differs"
             csum = got.reshape(got.shape[0], -1).astype(np.float64).sum(1)
@@ -61,9 +65,8 @@ class GoldenCase:
         # occupancy pattern must be identical (the cutoff is a 0.135-high step: SURVEY hazard 3)
         assert np.array_equal(got != 0, ref != 0), f"{self.name}: support differs in {((got != 0) != (ref != 0)).sum()} voxels"
         peak = max(1.0, float(np.abs(ref).max()))
-        tol = gauss_tol * (8 if self.cfg["mode"] == "features" else 1)
         err = float(np.abs(got - ref).max())
-        assert err <= tol * peak, f"{self.name}: max-abs {err} > {tol * peak}"
+        assert err <= gauss_tol * peak, f"{self.name}: max-abs {err} > {gauss_tol * peak}"
         return err
 
 
@@ -83,3 +86,43 @@ def ligand_batch(rng, B, num_types, vmin=40, vmax=60):
     coords = np.concatenate([random_walk_ligand(rng, int(c)) for c in counts], axis=0)
     types = rng.integers(0, num_types, size=int(offs[-1])).astype(np.int32)
     return offs, coords, types
+
+
+def import_reference():
+    """The live, unmodified reference package (offline install under baseline/_ref, which travels to the GPU box;
+    /root/reference in the build container).  Returns the module or None."""
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path in (os.path.join(root, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(path, "molvoxel")):
+            if path not in sys.path:
+                sys.path.insert(0, path)
+            try:
+                return importlib.import_module("molvoxel")
+            except Exception:
+                continue
+    return None
+
+
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11) in numpy:
+    counter (..., 4) uint32, key (..., 2) uint32 -> (..., 4) uint32.  Host restatement of csrc/mvx_rigid.cuh."""
+    c = [np.asarray(counter)[..., i].astype(np.uint64) for i in range(4)]
+    k = [np.asarray(key)[..., i].astype(np.uint64) for i in range(2)]
+    M0, M1, W0, W1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k[0], p1 & MASK, (p0 >> np.uint64(32)) ^ c[3] ^ k[1], p0 & MASK]
+        k = [(k[0] + W0) & MASK, (k[1] + W1) & MASK]
+    return np.stack(c, -1).astype(np.uint32)
+
+
+def philox_transform_uniforms(seed, mol_index):
+    """The six 53-bit uniforms (u1, u2, u3, tx, ty, tz) csrc/mvx_rigid.cuh:draw_rigid forms for one molecule."""
+    key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
+    w = [philox4x32_10(np.array([mol_index & 0xFFFFFFFF, (mol_index >> 32) & 0xFFFFFFFF, d, 0x6D767874], dtype=np.uint32), key)
+         for d in range(3)]
+    words = np.concatenate(w).astype(np.uint64)
+    u = [float(((words[2 * i] >> np.uint64(5)) << np.uint64(26)) | (words[2 * i + 1] >> np.uint64(6))) / 9007199254740992.0 for i in range(6)]
+    return u

@@ -5,7 +5,7 @@ import torch
 
 import molvoxel_b200 as mv
 from oracle import OracleVoxelizer, oracle_forward_batch
-from tests.helpers import GoldenCase, golden_names, ligand_batch
+from tests.helpers import GoldenCase, golden_names, import_reference, ligand_batch
 
 pytestmark = pytest.mark.gpu
 
@@ -53,44 +53,67 @@ def _compare(got, ref, binary_exact, tol=GAUSS_TOL):
     assert err <= tol * peak, f"max-abs {err} vs {tol * peak}"
 
 
+def _compare_chunked(out, oracle_chunk, B, chunk, binary_exact, tol=GAUSS_TOL):
+    """Compare a (B, C, D, D, D) CUDA grid with the oracle chunk by chunk (host memory stays bounded).  Returns the
+    largest max-abs / peak seen."""
+    worst = 0.0
+    for m0 in range(0, B, chunk):
+        m1 = min(B, m0 + chunk)
+        got, ref = out[m0:m1].cpu().numpy(), oracle_chunk(m0, m1)
+        _compare(got, ref, binary_exact, tol)
+        worst = max(worst, float(np.abs(got - ref).max()) / max(1.0, float(np.abs(ref).max())))
+    return worst
+
+
+def _sub_batch(offs, m0, m1, *per_atom):
+    a0, a1 = int(offs[m0]), int(offs[m1])
+    return (offs[m0:m1 + 1] - a0).astype(np.int32), [a[a0:a1] for a in per_atom]
+
+
 @pytest.mark.parametrize("density", ["binary", "gaussian"])
 def test_cfg3_ligand_batch_types_vs_oracle(density):
-    """BASELINE cfg 3 shape: 64^3, ~50-atom ligands, 4 types; binary must be bit-exact per molecule."""
+    """BASELINE cfg 3 at its stated size: 64^3, batch 1,024 ligands (~50 atoms), 4 types; binary bit-exact per molecule."""
     rng = np.random.default_rng(3)
-    B = 96
+    B = 1024
     offs, coords, types = ligand_batch(rng, B, 4)
     vox = mv.create_voxelizer(0.5, 64, "scalar", density, library="b200")
-    out = vox.forward_types_batch(coords, offs, None, types, 1.0, 4).cpu().numpy()
-    ref = oracle_forward_batch(0.5, 64, "scalar", density, 0.5, 8, "types", offs, coords, None, types, None, 4, 1.0,
-                               num_threads=8)
-    _compare(out, ref, density == "binary")
+    out = vox.forward_types_batch(coords, offs, None, types, 1.0, 4)
+    vox.check_status()
+
+    def oracle_chunk(m0, m1):
+        o, (c, t) = _sub_batch(offs, m0, m1, coords, types)
+        return oracle_forward_batch(0.5, 64, "scalar", density, 0.5, 8, "types", o, c, None, t, None, 4, 1.0, num_threads=16)
+    _compare_chunked(out, oracle_chunk, B, 128, density == "binary")
     # batch element == single call, bitwise (SURVEY App. A.6)
     for m in (0, B // 2, B - 1):
         a, b = offs[m], offs[m + 1]
-        one = vox.forward_types(coords[a:b], None, types[a:b], 1.0,
-                                out_grid=vox.get_empty_grid(4)).cpu().numpy()
-        assert np.array_equal(one, out[m])
+        one = vox.forward_types(coords[a:b], None, types[a:b], 1.0, out_grid=vox.get_empty_grid(4))
+        assert torch.equal(one, out[m])
 
 
 def test_cfg4_nine_channel_ligands_vs_oracle():
+    """BASELINE cfg 4 shape, 1,024 molecules against the oracle (parity sampled on >= 1,024 molecules)."""
     rng = np.random.default_rng(4)
-    B = 48
+    B = 1024
     offs, coords, types = ligand_batch(rng, B, 9)
     centers = rng.normal(scale=0.3, size=(B, 3))
     vox = mv.create_voxelizer(0.5, 64, "scalar", "gaussian", library="b200")
     out = vox.forward_types_batch(torch.from_numpy(coords).cuda(), torch.from_numpy(offs).cuda(),
                                   torch.from_numpy(centers).cuda(), torch.from_numpy(types).cuda(), 1.0, 9)
     vox.check_status()
-    ref = oracle_forward_batch(0.5, 64, "scalar", "gaussian", 0.5, 8, "types", offs, coords, centers, types, None, 9,
-                               1.0, num_threads=8)
-    _compare(out.cpu().numpy(), ref, False)
+
+    def oracle_chunk(m0, m1):
+        o, (c, t) = _sub_batch(offs, m0, m1, coords, types)
+        return oracle_forward_batch(0.5, 64, "scalar", "gaussian", 0.5, 8, "types", o, c, centers[m0:m1], t, None, 9, 1.0,
+                                    num_threads=16)
+    _compare_chunked(out, oracle_chunk, B, 64, False)
 
 
 @pytest.mark.parametrize("dense", [False, True], ids=["sparse_feats", "dense_feats"])
 def test_cfg2_pocket_features_vs_oracle(dense):
-    """BASELINE cfg 2 shape: ~2,000 atoms, C=16, 48^3 (batch shortened so the oracle finishes in seconds)."""
+    """BASELINE cfg 2 shape: ~2,000 atoms, C=16, 48^3, batch 32 against the oracle."""
     rng = np.random.default_rng(2)
-    B, V, C = 4, 2000, 16
+    B, V, C = 32, 2000, 16
     half = 0.5 * 47 / 2
     coords = rng.uniform(-half, half, size=(B * V, 3)).astype(np.float32).astype(np.float64)
     offs = np.arange(B + 1, dtype=np.int32) * V
@@ -101,24 +124,33 @@ def test_cfg2_pocket_features_vs_oracle(dense):
         feats[np.arange(B * V), rng.integers(0, 8, size=B * V)] = 1.0
         feats[:, 8:] = (rng.uniform(size=(B * V, 8)) < 0.25).astype(np.float32)
     vox = mv.create_voxelizer(0.5, 48, "scalar", "gaussian", library="b200")
-    out = vox.forward_features_batch(coords, offs, np.zeros((B, 3)), feats, 1.0).cpu().numpy()
-    ref = oracle_forward_batch(0.5, 48, "scalar", "gaussian", 0.5, 8, "features", offs, coords, np.zeros((B, 3)), None,
-                               feats, C, 1.0, num_threads=8)
-    _compare(out, ref, False, tol=GAUSS_TOL)
+    out = vox.forward_features_batch(coords, offs, np.zeros((B, 3)), feats, 1.0)
+
+    def oracle_chunk(m0, m1):
+        o, (c, f) = _sub_batch(offs, m0, m1, coords, feats)
+        return oracle_forward_batch(0.5, 48, "scalar", "gaussian", 0.5, 8, "features", o, c, np.zeros((m1 - m0, 3)), None,
+                                    f, C, 1.0, num_threads=16)
+    _compare_chunked(out, oracle_chunk, B, 16, False)
 
 
 def test_cfg5_large_complex_atomwise_vs_oracle():
-    """BASELINE cfg 5 shape: 96^3, res 0.375, C=32, atom-wise radii (atom count shortened for the oracle)."""
+    """BASELINE cfg 5 at its stated size: 10,000 atoms, 96^3, res 0.375, C=32, atom-wise radii U[1, 2]."""
     rng = np.random.default_rng(5)
-    V, C = 4000, 32
+    B, V, C = 2, 10000, 32
     half = 0.375 * 95 / 2
-    coords = rng.uniform(-half - 1, half + 1, size=(V, 3))
-    feats = rng.uniform(0, 1, size=(V, C)).astype(np.float32)
-    radii = rng.uniform(1.0, 2.0, size=V).astype(np.float32)
+    coords = rng.uniform(-half, half, size=(B * V, 3)).astype(np.float32).astype(np.float64)
+    offs = np.arange(B + 1, dtype=np.int32) * V
+    feats = rng.uniform(0, 1, size=(B * V, C)).astype(np.float32)
+    radii = rng.uniform(1.0, 2.0, size=B * V).astype(np.float32)
     vox = mv.create_voxelizer(0.375, 96, "atom-wise", "gaussian", library="b200")
-    out = vox.forward_features(coords, np.zeros(3), feats, radii).cpu().numpy()
-    ref = OracleVoxelizer(0.375, 96, "atom-wise", "gaussian").forward_features(coords, np.zeros(3), feats, radii)
-    _compare(out, ref, False, tol=GAUSS_TOL)
+    out = vox.forward_features_batch(coords, offs, np.zeros((B, 3)), feats, radii)
+    vox.check_status()
+
+    def oracle_chunk(m0, m1):
+        o, (c, f, r) = _sub_batch(offs, m0, m1, coords, feats, radii)
+        return oracle_forward_batch(0.375, 96, "atom-wise", "gaussian", 0.5, 8, "features", o, c, np.zeros((m1 - m0, 3)),
+                                    None, f, C, r, num_threads=16)
+    _compare_chunked(out, oracle_chunk, B, 2, False)
 
 
 def test_exact_mode_matches_oracle_blockdim_dim():
@@ -207,7 +239,6 @@ def test_random_transform_runs_and_preserves_mass():
     offs, coords, types = ligand_batch(rng, 8, 4)
     vox = mv.create_voxelizer(0.5, 64, "scalar", "binary", library="b200", blockdim=64)
     base = vox.forward_types_batch(coords, offs, None, types, 1.0, 4)
-    np.random.seed(0)
     aug = vox.forward_types_batch(coords, offs, None, types, 1.0, 4, random_translation=0.5, random_rotation=True)
     assert not torch.equal(base, aug)
     # rigid motion keeps every atom inside the 32 A box, so per-channel atom mass changes by < 20 %
@@ -256,22 +287,100 @@ def test_kernel_variants_agree_bitwise(kernel, monkeypatch):
     assert np.array_equal(out, ref)
 
 
-def test_fused_random_transform_matches_host_transform():
-    """The transform fused into the prep kernel == transforming on the host and voxelizing the result."""
-    from molvoxel_b200.transform import apply_transform, random_transform_params
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64_coords", "f32_coords"])
+@pytest.mark.parametrize("rt,rr", [(0.5, True), (0.0, True), (0.5, False)], ids=["rot_trans", "rot", "trans"])
+def test_fused_transform_is_the_reference_transform_bitwise(rt, rr, dtype):
+    """Explicit transforms (T objects drawn on the host) fused into the prep kernel == the reference's arithmetic
+    (numpy/transform.py:43-60, numpy/_quaternion.py:28-54) applied on the host and voxelized by the oracle: the
+    transformed coordinates are bit-identical (same operations, same dtype, no FMA), so binary grids are too."""
+    from molvoxel_b200.transform import RandomTransform, do_transform
     rng = np.random.default_rng(21)
-    offs, coords, types = ligand_batch(rng, 12, 4)
-    centers = rng.normal(scale=0.5, size=(12, 3))
-    vox = mv.create_voxelizer(0.5, 64, "scalar", "gaussian", library="b200")
+    B = 12
+    offs, coords, types = ligand_batch(rng, B, 4)
+    coords = coords.astype(dtype)
+    centers = rng.normal(scale=0.5, size=(B, 3)).astype(dtype)
     np.random.seed(7)
-    aug = vox.forward_types_batch(coords, offs, centers, types, 1.0, 4, random_translation=0.5, random_rotation=True)
-    np.random.seed(7)
-    moved, _ = apply_transform(coords, offs, centers, random_transform_params(12, 0.5, True))
-    ref = oracle_forward_batch(0.5, 64, "scalar", "gaussian", 0.5, 8, "types", offs, moved, None, types, None, 4, 1.0,
-                               num_threads=8)
-    got = aug.cpu().numpy()
-    assert float(np.abs(got - ref).max()) <= 0.14   # at most a cutoff tie flipped by 1e-16 coordinate noise ...
-    assert (np.abs(got - ref) > 1e-5).sum() <= 2     # ... in at most a couple of voxels
+    ts = [RandomTransform(rt, rr).get_transform() for _ in range(B)]
+    moved = np.concatenate([do_transform(coords[offs[m]:offs[m + 1]] - centers[m].reshape(1, 3), None, ts[m].translation,
+                                         ts[m].quaternion) for m in range(B)])
+    assert moved.dtype == dtype
+    for density in ("binary", "gaussian"):
+        vox = mv.create_voxelizer(0.5, 64, "scalar", density, library="b200")
+        for dev_in in (False, True):
+            args = [torch.from_numpy(a).cuda() for a in (coords, offs, centers, types)] if dev_in else [coords, offs, centers, types]
+            got = vox.forward_types_batch(*args, 1.0, 4, transforms=ts).cpu().numpy()
+            ref = oracle_forward_batch(0.5, 64, "scalar", density, 0.5, 8, "types", offs, moved, None, types, None, 4, 1.0,
+                                       num_threads=8)
+            _compare(got, ref, density == "binary")
+    # the torch backend's single translation (torch/transform.py:56-60) on request
+    once = mv.create_voxelizer(0.5, 64, "scalar", "binary", library="b200", translate_once=True)
+    moved1 = np.concatenate([do_transform(coords[offs[m]:offs[m + 1]] - centers[m].reshape(1, 3), None, ts[m].translation,
+                                          ts[m].quaternion, translate_once=True) for m in range(B)])
+    got = once.forward_types_batch(coords, offs, centers, types, 1.0, 4, transforms=ts).cpu().numpy()
+    ref = oracle_forward_batch(0.5, 64, "scalar", "binary", 0.5, 8, "types", offs, moved1, None, types, None, 4, 1.0, num_threads=8)
+    assert np.array_equal(got, ref)
+
+
+def test_device_generator_matches_its_host_restatement():
+    """The (quaternion, translation) rows the prep kernel draws (mvx_random_transforms = the same device function)
+    against a numpy restatement of Philox4x32-10 + the reference's formulas (numpy/_quaternion.py:13-21,
+    numpy/transform.py:74-76): translations exactly, quaternions to 4 ulp (device sincos vs libm)."""
+    import math
+    from tests.helpers import philox_transform_uniforms
+    vox = mv.create_voxelizer(0.5, 32, "scalar", "binary", library="b200", seed=0x1234_5678_9ABC_DEF0)
+    B, off, rt = 64, (1 << 33) + 5, 0.5
+    rows = vox.random_transforms(B, rt, True, rng_offset=off).cpu().numpy()
+    for m in range(B):
+        u1, u2, u3, tx, ty, tz = philox_transform_uniforms(0x1234_5678_9ABC_DEF0, off + m)
+        t = np.array([-rt + (rt - -rt) * u for u in (tx, ty, tz)]).astype(np.float32).astype(np.float64)
+        assert np.array_equal(rows[m, 4:], t)
+        a, b = math.sqrt(1 - u1), math.sqrt(u1)
+        q = np.array([a * math.sin(2 * math.pi * u2), a * math.cos(2 * math.pi * u2), b * math.sin(2 * math.pi * u3), b * math.cos(2 * math.pi * u3)])
+        assert np.abs(rows[m, :4] - q).max() <= 1e-15
+    q = rows[:, :4]
+    assert np.abs((q * q).sum(1) - 1.0).max() < 1e-14 and np.abs(rows[:, 4:]).max() <= rt
+    # rotation only / translation only leave the other part at identity / zero
+    r_only = vox.random_transforms(B, 0.0, True, rng_offset=off).cpu().numpy()
+    t_only = vox.random_transforms(B, rt, False, rng_offset=off).cpu().numpy()
+    assert np.array_equal(r_only[:, :4], rows[:, :4]) and not r_only[:, 4:].any()
+    assert np.array_equal(t_only[:, 4:], rows[:, 4:]) and np.array_equal(t_only[:, :4], np.tile([1.0, 0, 0, 0], (B, 1)))
+
+
+@pytest.mark.parametrize("dense", [False, True], ids=["ligands_cells", "pockets_pipe"])
+def test_device_drawn_transforms_equal_explicit_rows_and_any_sharding(dense):
+    """Fused device RNG == passing the same rows explicitly (bitwise), and the augmentation of a molecule depends only
+    on (seed, global molecule index): chunks / shards of a sweep reproduce the whole batch."""
+    rng = np.random.default_rng(33)
+    if dense:
+        B, V, dim = 6, 1800, 40
+        offs = np.arange(B + 1, dtype=np.int32) * V
+        coords = rng.uniform(-9, 9, size=(B * V, 3))
+        types = rng.integers(0, 4, size=B * V).astype(np.int32)
+    else:
+        B, dim = 40, 64
+        offs, coords, types = ligand_batch(rng, B, 4)
+    centers = rng.normal(scale=0.3, size=(B, 3))
+    vox = mv.create_voxelizer(0.5, dim, "scalar", "gaussian", library="b200", seed=99)
+    whole = vox.forward_types_batch(coords, offs, centers, types, 1.0, 4, random_translation=0.5, random_rotation=True,
+                                    rng_offset=1000)
+    rows = vox.random_transforms(B, 0.5, True, rng_offset=1000)
+    explicit = vox.forward_types_batch(coords, offs, centers, types, 1.0, 4, random_translation=0.5, random_rotation=True,
+                                       transforms=rows.cpu().numpy())
+    assert torch.equal(whole, explicit)
+    plain = vox.forward_types_batch(coords, offs, centers, types, 1.0, 4)
+    assert not torch.equal(whole, plain)
+    for m0, m1 in ((0, B // 3), (B // 3, B)):   # two shards with their global offsets
+        o, (c, t) = _sub_batch(offs, m0, m1, coords, types)
+        part = vox.forward_types_batch(c, o, centers[m0:m1], t, 1.0, 4, random_translation=0.5, random_rotation=True,
+                                       rng_offset=1000 + m0)
+        assert torch.equal(part, whole[m0:m1])
+    # the internal molecule counter continues across calls: two calls draw different transforms, a re-seed repeats them
+    vox.seed(5)
+    a = vox.forward_types_batch(coords, offs, centers, types, 1.0, 4, random_rotation=True)
+    b = vox.forward_types_batch(coords, offs, centers, types, 1.0, 4, random_rotation=True)
+    vox.seed(5)
+    c = vox.forward_types_batch(coords, offs, centers, types, 1.0, 4, random_rotation=True)
+    assert not torch.equal(a, b) and torch.equal(a, c)
 
 
 def test_pipelined_host_path_matches_blocking():
@@ -404,8 +513,11 @@ def test_randomized_configs_vs_oracle(seed, kernel, monkeypatch):
     else:
         radii = rng.uniform(0.4 * rmax, rmax, size=C).astype(np.float32)
     types = rng.integers(0, C, size=N).astype(np.int32) if mode == "types" else None
+    # signed features can cancel to an exact 0 in one summation order and to 1e-9 in another: the support check below
+    # needs non-negative rows, so only every other seed carries signs
+    signed = seed % 2 == 1
     feats = (rng.integers(0, 4, size=(N, C)).astype(np.float32) if density == "binary"
-             else rng.uniform(-1, 1, size=(N, C)).astype(np.float32)) if mode == "features" else None
+             else rng.uniform(-1 if signed else 0, 1, size=(N, C)).astype(np.float32)) if mode == "features" else None
     vox = mv.create_voxelizer(res, dim, radii_type, density, library="b200", blockdim=bd, sigma=sigma)
     if mode == "types":
         out = vox.forward_types_batch(coords, offs, centers, types, radii, C)
@@ -421,7 +533,7 @@ def test_randomized_configs_vs_oracle(seed, kernel, monkeypatch):
         assert np.array_equal(got, ref), f"{(got != ref).sum()} voxels differ"
     else:
         peak = max(1.0, float(np.abs(ref).max()))
-        if mode != "features":
+        if mode != "features" or not signed:
             assert np.array_equal(got != 0, ref != 0)
         assert float(np.abs(got - ref).max()) <= GAUSS_TOL * peak
 
@@ -756,7 +868,7 @@ def test_randomized_dense_configs_vs_oracle(seed, kernel, monkeypatch):
     else:
         peak = max(1.0, float(np.abs(ref).max()))
         assert np.array_equal(got != 0, ref != 0)
-        assert float(np.abs(got - ref).max()) <= 8 * GAUSS_TOL * peak
+        assert float(np.abs(got - ref).max()) <= GAUSS_TOL * peak
     if seed % 3 == 0:   # bf16 grid == the fp32 grid rounded once
         low = mv.create_voxelizer(res, dim, radii_type, density, library="b200", blockdim=bd, out_dtype=torch.bfloat16)
         if mode == "types":
@@ -813,3 +925,61 @@ def test_sharded_batches_equal_the_whole_batch():
             lo, (c, t), (z,) = shard_batch(offs, rank, 3, coords, types, per_mol=(centers,))
             parts.append(vox.forward_types_batch(c, lo, z, t, 1.1, 6).clone())
         assert torch.equal(torch.cat(parts, 0), whole)
+
+
+_REF = import_reference()
+needs_ref = pytest.mark.skipif(_REF is None, reason="reference package not available (baseline/_ref)")
+
+
+@needs_ref
+@pytest.mark.parametrize("density", ["binary", "gaussian"])
+def test_cuda_matches_live_reference_ligands(density):
+    """The CUDA path against the LIVE numpy backend (not the oracle) on 48 ligands, 64^3, 9 types, incl. the reference's
+    own batched use-case (test/test_time_numpy.py:11-15): random_translation=0.5, random_rotation=True drawn from
+    numpy's global RNG — rng="numpy" reproduces the stream, so the grids are comparable molecule by molecule."""
+    rng = np.random.default_rng(77)
+    B, C = 48, 9
+    offs, coords, types = ligand_batch(rng, B, C)
+    centers = np.stack([coords[offs[m]:offs[m + 1]].mean(0) for m in range(B)])
+    ref_vox = _REF.create_voxelizer(0.5, 64, "scalar", density, library="numpy")
+    for rt, rr in ((0.0, False), (0.5, True)):
+        np.random.seed(2026)
+        ref = np.stack([ref_vox.forward_types(coords[offs[m]:offs[m + 1]], centers[m], types[offs[m]:offs[m + 1]].astype(np.int16),
+                                              1.0, rt, rr, out_grid=ref_vox.get_empty_grid(C)) for m in range(B)])
+        vox = mv.create_voxelizer(0.5, 64, "scalar", density, library="b200", rng="numpy")
+        np.random.seed(2026)
+        got = vox.forward_types_batch(coords, offs, centers, types, 1.0, C, random_translation=rt, random_rotation=rr)
+        vox.check_status()
+        _compare(got.cpu().numpy(), ref, density == "binary")
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(32))
+def test_cuda_matches_live_reference_random_configs(seed):
+    """Random configurations (the CPU fuzz of tests/test_live_reference.py) straight against the live reference."""
+    from tests.test_live_reference import random_case, run
+    c = random_case(seed)
+    kw = {} if c["bd"] is None else {"blockdim": c["bd"]}
+    ref = run(_REF.create_voxelizer(c["res"], c["dim"], c["radii_type"], c["density"], library="numpy", sigma=c["sigma"], **kw), c)
+    vox = mv.create_voxelizer(c["res"], c["dim"], c["radii_type"], c["density"], library="b200", blockdim=c["bd"], sigma=c["sigma"])
+    got = run(vox, c)
+    vox.check_status()
+    _compare(got.cpu().numpy(), ref, c["density"] == "binary" and c["mode"] != "features")
+
+
+@needs_ref
+def test_cuda_matches_live_reference_pocket_features():
+    """forward_features, 48^3, 2,000-atom pocket, C=16 (cfg 2 shape) against the live numpy backend, incl. augmentation."""
+    rng = np.random.default_rng(78)
+    V, C = 2000, 16
+    half = 0.5 * 47 / 2
+    coords = rng.uniform(-half, half, size=(V, 3))
+    feats = rng.uniform(0, 1, size=(V, C)).astype(np.float32)
+    ref_vox = _REF.create_voxelizer(0.5, 48, "scalar", "gaussian", library="numpy")
+    vox = mv.create_voxelizer(0.5, 48, "scalar", "gaussian", library="b200", rng="numpy")
+    for rt, rr in ((0.0, False), (0.5, True)):
+        np.random.seed(9)
+        ref = ref_vox.forward_features(coords, np.zeros(3), feats, 1.0, rt, rr)
+        np.random.seed(9)
+        got = vox.forward_features(coords, np.zeros(3), feats, 1.0, rt, rr)
+        _compare(got.cpu().numpy(), ref, False)
