@@ -164,6 +164,18 @@ int mvx_profile_end(double *ms_prep, double *ms_bin, double *ms_voxelize, int *n
 int mvx_random_transforms(uint64_t rng_seed, uint64_t rng_offset, int32_t num_mols, int32_t transform_flags,
                           double random_translation, double *out, void *stream);
 
+/*
+ * Synthetic ligands of the virtual-screening sweep (V ~ U{vmin..vmax} atoms, a 3-D random walk
+ * with `step` Angstrom steps recentred to the origin, fp32-representable coordinates, types uniform over num_types),
+ * generated on the DEVICE from the same counter-based generator keyed by (seed, first_mol + molecule index): any
+ * sharding or chunking of a sweep sees the same molecules.  Benchmark / test input, not part of the hot path.
+ * Pass 1 (mol_offsets == NULL): writes counts[num_mols].  Pass 2 (mol_offsets = exclusive prefix sums of the counts,
+ * num_mols + 1 entries, relative to the first molecule): writes coords (N,3) of coords_dtype and types (N) (or NULL).
+ */
+int mvx_synth_ligands(uint64_t seed, uint64_t first_mol, int32_t num_mols, int32_t vmin, int32_t vmax, int32_t num_types,
+                      double step, const int32_t *mol_offsets, int32_t *counts, void *coords, int32_t coords_dtype,
+                      int32_t *types, void *stream);
+
 const char *mvx_last_error(void);
 int mvx_version(void);
 

@@ -17,7 +17,7 @@ OBJ_DIR = os.path.join(CSRC, "_obj")
 API_SOURCE = os.path.join(CSRC, "mvx_api.cu")
 INST_SOURCE = os.path.join(CSRC, "mvx_vox_inst.cu")
 SOURCES = [API_SOURCE, INST_SOURCE]
-HEADERS = [os.path.join(CSRC, h) for h in ("mvx_common.cuh", "mvx_bin_kernels.cuh", "mvx_vox_kernels.cuh", "mvx_launch.cuh")] + \
+HEADERS = [os.path.join(CSRC, h) for h in ("mvx_common.cuh", "mvx_rigid.cuh", "mvx_bin_kernels.cuh", "mvx_vox_kernels.cuh", "mvx_launch.cuh")] + \
           [os.path.join(os.path.dirname(_HERE), "include", "molvoxel_b200.h")]
 # (mode, channel chunk) pairs the voxelize kernels are instantiated for (x binary / gaussian): mvx_api.cu:launch_vox
 INSTANCES = [(0, 1)] + [(m, ch) for m in (1, 2) for ch in (1, 4, 8, 12, 16)]
@@ -150,6 +150,9 @@ def lib():
         L.mvx_voxelize_form.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch)]
         L.mvx_random_transforms.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, vp, vp]
         L.mvx_random_transforms.restype = ctypes.c_int
+        L.mvx_synth_ligands.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                        ctypes.c_int32, ctypes.c_double, vp, vp, vp, ctypes.c_int32, vp, vp]
+        L.mvx_synth_ligands.restype = ctypes.c_int
         L.mvx_profile_begin.argtypes = [ctypes.c_int]
         dp = ctypes.POINTER(ctypes.c_double)
         L.mvx_profile_end.argtypes = [dp, dp, dp, ctypes.POINTER(ctypes.c_int)]
@@ -164,7 +167,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "mvx_version", "mvx_last_error", "mvx_workspace_bytes", "mvx_host_staging_bytes", "mvx_voxelize",
     "mvx_voxelize_host", "mvx_check_status", "mvx_launches_per_call", "mvx_voxelize_form", "mvx_profile_begin",
-    "mvx_profile_end", "mvx_random_transforms",
+    "mvx_profile_end", "mvx_random_transforms", "mvx_synth_ligands",
 ]
 
 

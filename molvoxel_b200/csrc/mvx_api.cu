@@ -506,6 +506,23 @@ int mvx_random_transforms(uint64_t rng_seed, uint64_t rng_offset, int32_t num_mo
     return MVX_OK;
 }
 
+int mvx_synth_ligands(uint64_t seed, uint64_t first_mol, int32_t num_mols, int32_t vmin, int32_t vmax, int32_t num_types,
+                      double step, const int32_t* mol_offsets, int32_t* counts, void* coords, int32_t coords_dtype,
+                      int32_t* types, void* stream) {
+    if (num_mols < 0 || vmin < 1 || vmax < vmin || num_types < 1) return fail(MVX_ERR_BAD_SHAPE, "bad synthetic-ligand shape");
+    if (num_mols == 0) return MVX_OK;
+    if (!mol_offsets && !counts) return fail(MVX_ERR_NULL_POINTER, "counts / mol_offsets");
+    if (mol_offsets && !coords) return fail(MVX_ERR_NULL_POINTER, "coords");
+    if (coords_dtype != MVX_F32 && coords_dtype != MVX_F64) return fail(MVX_ERR_BAD_ENUM, "coords_dtype");
+    mvx::SynthParams sp;
+    sp.seed = seed; sp.first_mol = first_mol; sp.B = num_mols; sp.vmin = vmin; sp.vmax = vmax; sp.num_types = num_types;
+    sp.coords_f64 = coords_dtype == MVX_F64; sp.step = step; sp.mol_offsets = mol_offsets; sp.counts = counts;
+    sp.coords = coords; sp.types = types;
+    mvx::mvx_synth_ligands_kernel<<<(unsigned)((num_mols + 127) / 128), 128, 0, (cudaStream_t)stream>>>(sp);
+    MVX_CUDA_OK(cudaGetLastError());
+    return MVX_OK;
+}
+
 int mvx_profile_begin(int max_calls) {
     if (g_prof.active) return fail(MVX_ERR_UNSUPPORTED, "a profile is already open on this thread");
     if (max_calls < 1) return fail(MVX_ERR_BAD_SHAPE, "max_calls must be >= 1");

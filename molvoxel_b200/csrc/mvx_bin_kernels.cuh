@@ -653,6 +653,49 @@ __global__ void __launch_bounds__(128) mvx_draw_transforms_kernel(const DrawPara
     o[4] = R.t[0]; o[5] = R.t[1]; o[6] = R.t[2];
 }
 
+// Synthetic sweep ligands (see mvx_rigid.cuh): one thread per molecule.
+__global__ void __launch_bounds__(128) mvx_synth_ligands_kernel(const SynthParams P) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= P.B) return;
+    const unsigned long long gmol = P.first_mol + (unsigned long long)m;
+    const int V = synth_count(P.seed, gmol, P.vmin, P.vmax);
+    if (P.counts != nullptr) P.counts[m] = V;
+    if (P.mol_offsets == nullptr) return;
+    const int a0 = P.mol_offsets[m];
+    const uint32_t k0 = (uint32_t)P.seed, k1 = (uint32_t)(P.seed >> 32);
+    auto step_of = [&](int a, double (&d)[3], uint32_t& tw) {
+        uint32_t w[4];
+        philox4x32_10((uint32_t)gmol, (uint32_t)(gmol >> 32), (uint32_t)(a + 1), kSynthDomain, k0, k1, w);
+        const double z = 2.0 * ((double)w[0] * (1.0 / 4294967296.0)) - 1.0;   // uniform direction on the sphere
+        const double rho = sqrt(fmax(0.0, 1.0 - z * z));
+        double sn, cs;
+        sincospi(2.0 * ((double)w[1] * (1.0 / 4294967296.0)), &sn, &cs);
+        d[0] = P.step * rho * cs; d[1] = P.step * rho * sn; d[2] = P.step * z;
+        tw = w[2];
+    };
+    double sum[3] = {0.0, 0.0, 0.0}, pos[3] = {0.0, 0.0, 0.0};
+    for (int a = 0; a < V; ++a) {   // pass 1: centroid of the walk
+        double d[3]; uint32_t tw;
+        step_of(a, d, tw);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { pos[k] += d[k]; sum[k] += pos[k]; }
+    }
+    const double mean[3] = {sum[0] / V, sum[1] / V, sum[2] / V};
+    pos[0] = pos[1] = pos[2] = 0.0;
+    for (int a = 0; a < V; ++a) {   // pass 2: recentred, rounded to fp32-representable values
+        double d[3]; uint32_t tw;
+        step_of(a, d, tw);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            pos[k] += d[k];
+            const float v = (float)(pos[k] - mean[k]);
+            if (P.coords_f64) reinterpret_cast<double*>(P.coords)[3 * (size_t)(a0 + a) + k] = (double)v;
+            else reinterpret_cast<float*>(P.coords)[3 * (size_t)(a0 + a) + k] = v;
+        }
+        if (P.types != nullptr) P.types[a0 + a] = (int32_t)(tw % (uint32_t)P.num_types);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // voxelize, precision = 64 (the reference's `precision=64` constructor argument, numpy/voxelizer.py:28-34; SURVEY
 // row f4): distances, dr = dist / r, the Gaussian and the accumulation all in fp64, (B, Cout, D, D, D) float64 out.

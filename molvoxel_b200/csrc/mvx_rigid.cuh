@@ -109,6 +109,30 @@ __device__ __forceinline__ void apply_rigid(F (&p)[3], const Rigid& R, const int
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Synthetic ligands of the virtual-screening sweep (SURVEY.md section 8d, cfg3 / cfg4 recipe), generated on the
+// device and keyed by the GLOBAL molecule index, so any sharding or chunking of the sweep sees the same molecules:
+// V ~ U{vmin..vmax} atoms, a 3-D random walk with `step` Angstrom steps recentred to the origin, coordinates rounded
+// to fp32-representable values, types uniform over num_types.  Benchmark / test input only — not on the hot path.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kSynthDomain = 0x6D767873u;   // "mvxs"
+
+__host__ __device__ __forceinline__ int synth_count(uint64_t seed, uint64_t gmol, int vmin, int vmax) {
+    uint32_t w[4];
+    philox4x32_10((uint32_t)gmol, (uint32_t)(gmol >> 32), 0u, kSynthDomain, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+    return vmin + (int)(w[0] % (uint32_t)(vmax - vmin + 1));
+}
+
+struct SynthParams {
+    unsigned long long seed, first_mol;
+    int B, vmin, vmax, num_types, coords_f64;
+    double step;
+    const int32_t* mol_offsets;   // (B+1), relative to the first molecule; nullptr: only counts are written
+    int32_t* counts;              // (B) or nullptr
+    void* coords;                 // (N,3) f32 | f64
+    int32_t* types;               // (N) or nullptr
+};
+
 struct DrawParams {
     unsigned long long seed, offset;
     int B, flags;

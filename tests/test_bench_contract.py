@@ -23,6 +23,11 @@ def test_reference_arm_prints_one_json_line_with_contract_keys():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert "workload" in d["config"]
+    # both arms print the same config keys for the same arguments
+    class A:   # noqa: N801
+        workload, batch, augment, out_dtype, molecules = "cfg3", 0, False, "float32", 0
+    assert d["config"] == bench.workload_config(A, 1)
+    assert d["config"]["molecules"] == 262_144 and d["scaling"] == "strong"
 
 
 def test_reference_arm_other_ranks_exit_silently():

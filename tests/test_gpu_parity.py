@@ -983,3 +983,41 @@ def test_cuda_matches_live_reference_pocket_features():
         np.random.seed(9)
         got = vox.forward_features(coords, np.zeros(3), feats, 1.0, rt, rr)
         _compare(got.cpu().numpy(), ref, False)
+
+
+def test_synthetic_sweep_ligands_are_keyed_by_molecule_index():
+    """mvx_synth_ligands (the cfg4 sweep's input generator): counts follow the host restatement of the generator,
+    molecules depend only on (seed, global index) — any chunking gives the same atoms —, coordinates are
+    fp32-representable recentred 1.5 A random walks, types cover [0, C)."""
+    import ctypes
+    from molvoxel_b200 import _lib
+    from tests.helpers import philox4x32_10
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    seed, first, B, C = 4, (1 << 32) + 123, 300, 9
+
+    def gen(first_mol, n):
+        counts = torch.empty(n, dtype=torch.int32, device=dev)
+        _lib.raise_for_status(L.mvx_synth_ligands(seed, first_mol, n, 40, 60, C, 1.5, None, ctypes.c_void_p(counts.data_ptr()), None, 1, None, None))
+        offs = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+        offs[1:] = torch.cumsum(counts, 0)
+        N = int(offs[-1])
+        coords = torch.empty((N, 3), dtype=torch.float64, device=dev)
+        types = torch.empty(N, dtype=torch.int32, device=dev)
+        _lib.raise_for_status(L.mvx_synth_ligands(seed, first_mol, n, 40, 60, C, 1.5, ctypes.c_void_p(offs.data_ptr()), None,
+                                                  ctypes.c_void_p(coords.data_ptr()), 1, ctypes.c_void_p(types.data_ptr()), None))
+        torch.cuda.synchronize()
+        return offs.cpu().numpy(), coords.cpu().numpy(), types.cpu().numpy()
+    offs, coords, types = gen(first, B)
+    counts = np.diff(offs)
+    for m in (0, 1, B - 1):
+        g = first + m
+        w = philox4x32_10(np.array([g & 0xFFFFFFFF, g >> 32, 0, 0x6D767873], dtype=np.uint32), np.array([seed, 0], dtype=np.uint32))
+        assert counts[m] == 40 + int(w[0]) % 21
+    assert counts.min() >= 40 and counts.max() <= 60 and types.min() == 0 and types.max() == C - 1
+    assert np.array_equal(coords, coords.astype(np.float32).astype(np.float64))
+    m0 = coords[offs[5]:offs[6]]
+    assert np.abs(m0.mean(0)).max() < 1e-5 and np.allclose(np.linalg.norm(np.diff(m0, axis=0), axis=1), 1.5, atol=1e-4)
+    o2, c2, t2 = gen(first + 100, 50)   # a chunk that starts elsewhere sees the same molecules
+    a0, a1 = offs[100], offs[150]
+    assert np.array_equal(c2, coords[a0:a1]) and np.array_equal(t2, types[a0:a1]) and np.array_equal(o2, offs[100:151] - a0)
