@@ -728,18 +728,20 @@ __device__ __forceinline__ void tiles_body(const VoxParams& P, const int tile_id
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) off[k] = row_off || dzf == k;
                             }
-                            // |s - r^2| <= tau (slightly widened) for any of the 4 voxels -> replay in fp64
-                            const float r2c = 0.5f * (A.w + Bv.x), tauh = 0.5f * (A.w - Bv.x) * 1.0001f + 1e-12f;
-                            float sk[4], w[4], dmin = 3.0e38f;
+                            // r^2 - tau <= s <= r^2 + tau for any of the 4 voxels -> replay in fp64.  Two direct compares
+                            // per voxel: a |s - r^2| <= tau form loses voxels whose s rounds onto the band's lower edge
+                            // (the midpoint and half-width of two fp32 numbers next to 1.0 carry 0.2 % of rounding error)
+                            float sk[4], w[4];
+                            bool band = false;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const float dz = A.z - oz[k];
                                 sk[k] = fmaf(dz, dz, dxy);
                                 w[k] = (sk[k] < Bv.x && !off[k]) ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
-                                dmin = fminf(dmin, fabsf(sk[k] - r2c));
+                                band = band || (sk[k] >= Bv.x && sk[k] <= A.w);
                             }
                             const float4* ent = sE + (int)wI[j] * ES4;
-                            if (dmin <= tauh) {   // rare
+                            if (band) {   // rare
                                 const int n = (int)__float_as_uint(ent[2].x);
                                 const float r32 = (MODE == 1) ? P.recs[n].r : Bv.w;
 #pragma unroll
@@ -1173,18 +1175,19 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
                             const float4 Bv = lds128(eb + 16u);
                             const float dx = A.x - ox, dy = A.y - oy;
                             const float dxy = fmaf(dx, dx, dy * dy);
-                            // |s - r^2| <= tau (slightly widened) for any of the 4 voxels -> replay in fp64
-                            const float r2c = 0.5f * (A.w + Bv.x), tauh = 0.5f * (A.w - Bv.x) * 1.0001f + 1e-12f;
-                            float sk[4], w[4], dmin = 3.0e38f;
+                            // r^2 - tau <= s <= r^2 + tau for any of the 4 voxels -> replay in fp64 (two direct compares
+                            // per voxel: see the tile form)
+                            float sk[4], w[4];
+                            bool band = false;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const float dz = A.z - oz[k];
                                 sk[k] = fmaf(dz, dz, dxy);
                                 w[k] = (sk[k] < Bv.x) ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
-                                dmin = fminf(dmin, fabsf(sk[k] - r2c));
+                                band = band || (sk[k] >= Bv.x && sk[k] <= A.w);
                             }
                             const uint32_t forb = __float_as_uint(Bv.z);
-                            if (dmin <= tauh || forb != kNoForb) {   // rare: tolerance band, or a block-cull plane in reach
+                            if (band || forb != kNoForb) {   // rare: tolerance band, or a block-cull plane in reach
                                 bool off[4];
                                 {   // block-cull emulation: voxels on the atom's forbidden planes take nothing from it
                                     const uint32_t tx = forb ^ lane_key;
@@ -1193,7 +1196,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
 #pragma unroll
                                     for (int k = 0; k < 4; ++k) off[k] = row_off || dzf == k;
                                 }
-                                if (dmin <= tauh) {
+                                if (band) {
                                     const int n = (int)lds32(eb + 32u);
                                     const float r32 = (MODE == 1) ? P.recs[n].r : Bv.w;
 #pragma unroll

@@ -1021,3 +1021,30 @@ def test_synthetic_sweep_ligands_are_keyed_by_molecule_index():
     o2, c2, t2 = gen(first + 100, 50)   # a chunk that starts elsewhere sees the same molecules
     a0, a1 = offs[100], offs[150]
     assert np.array_equal(c2, coords[a0:a1]) and np.array_equal(t2, types[a0:a1]) and np.array_equal(o2, offs[100:151] - a0)
+
+
+@pytest.mark.parametrize("kernel", ["pipe", "tiles", "cells", "rows"])
+def test_pairs_on_the_edges_of_the_tolerance_band(kernel, monkeypatch):
+    """Atom-voxel pairs whose squared distance sits within a few ulp of r^2 - tau / r^2 + tau (the edges of the band inside
+    which the kernels replay the reference's fp64 arithmetic): every form must still take the reference's decision.
+    Regression: the layered forms used a |s - r^2| <= tau test whose midpoint / half-width rounding dropped true hits that
+    rounded onto the lower edge (found by bench.py's in-run parity sample on full-size cfg2 batches)."""
+    monkeypatch.setenv("MVX_KERNEL", kernel)
+    rng = np.random.default_rng(99)
+    D, res, r, V = 48, 0.5, 1.0, 6000
+    half = res * (D - 1) / 2
+    ext = D * res + r
+    tau = r * 21.0 * 2.0 ** -24 * ext + r * r * 12.0 * 2.0 ** -24     # mvx_api.cu:make_plan
+    axis = np.arange(D) * res - half
+    g = axis[rng.integers(6, D - 6, size=(V, 3))]
+    u = rng.normal(size=(V, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    edge = np.where(rng.uniform(size=V) < 0.7, r * r - tau, r * r + tau)
+    d = np.sqrt(edge * (1.0 + rng.uniform(-4e-8, 4e-8, size=V) * rng.integers(0, 4, size=V)))
+    coords = (g + u * d[:, None]).astype(np.float32).astype(np.float64)
+    feats = rng.integers(1, 4, size=(V, 4)).astype(np.float32)
+    for density in ("binary", "gaussian"):
+        vox = mv.create_voxelizer(res, D, "scalar", density, library="b200")
+        got = vox.forward_features(coords, None, feats, r).cpu().numpy()
+        ref = OracleVoxelizer(res, D, "scalar", density).forward_features(coords, None, feats, r)
+        _compare(got, ref, density == "binary")
