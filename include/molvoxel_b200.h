@@ -157,6 +157,19 @@ int mvx_profile_begin(int max_calls);
 int mvx_profile_end(double *ms_prep, double *ms_bin, double *ms_voxelize, int *num_calls);
 
 /*
+ * Brick compaction for host-side consumers (a ligand grid is >= 97 % zeros; copying it to the host densely measures
+ * PCIe).  After mvx_voxelize(spec, batch, grids, workspace, ...) — float32 grids — on the same stream: every brick of
+ * 8 x 8 x 8 voxels of one channel that holds a non-zero value is copied to brick_vals[slot] (512 floats, brick-local
+ * [x][y][z], zero-padded where it sticks out of the grid) and brick_ids[slot] = ((mol * out_channels + c) * ncol + col) *
+ * nbz + bz, with ncol = ceil(D/8)^2 columns (col = bx * ceil(D/8) + by) and nbz = ceil(D/8).  Slot order is arbitrary.
+ * *count receives the number of non-empty bricks; if it exceeds `capacity` the surplus was dropped (call again with
+ * larger buffers).  `workspace` = the voxelize call's workspace (its column occupancy lets empty columns be skipped
+ * without reading them) or NULL (every column is read).  All pointers are DEVICE pointers.
+ */
+int mvx_compact_bricks(const mvx_grid_spec *spec, const mvx_batch *batch, const void *grids, const void *workspace,
+                       uint32_t *brick_ids, float *brick_vals, uint32_t capacity, uint32_t *count, void *stream);
+
+/*
  * The rigid transforms mvx_voxelize draws on the device for molecules [rng_offset, rng_offset + num_mols) with these
  * (rng_seed, transform_flags, random_translation): writes (num_mols, 7) f64 rows (quaternion, translation) to the
  * DEVICE buffer `out` on `stream`.  Passing them back as mvx_batch.transforms gives bit-identical grids.

@@ -15,11 +15,12 @@ from .voxelizer import Voxelizer
 from .sharding import shard_bounds, shard_batch, gather_grids
 from .pointcloud import PointCloud, Collator, collate, mol_point_cloud, system_point_cloud
 from .dx import write_grid_to_dx_file
+from .sparse import SparseGrids
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 __all__ = ["create_voxelizer", "create_random_transform", "Voxelizer", "RandomTransform", "T",
            "shard_bounds", "shard_batch", "gather_grids", "PointCloud", "Collator", "collate", "mol_point_cloud",
-           "system_point_cloud", "write_grid_to_dx_file"]
+           "system_point_cloud", "write_grid_to_dx_file", "SparseGrids"]
 
 
 def create_random_transform(random_translation: float = 0.0, random_rotation: bool = False,

@@ -153,6 +153,8 @@ def lib():
         L.mvx_synth_ligands.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.c_int32, ctypes.c_double, vp, vp, vp, ctypes.c_int32, vp, vp]
         L.mvx_synth_ligands.restype = ctypes.c_int
+        L.mvx_compact_bricks.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch), vp, vp, vp, vp, ctypes.c_uint32, vp, vp]
+        L.mvx_compact_bricks.restype = ctypes.c_int
         L.mvx_profile_begin.argtypes = [ctypes.c_int]
         dp = ctypes.POINTER(ctypes.c_double)
         L.mvx_profile_end.argtypes = [dp, dp, dp, ctypes.POINTER(ctypes.c_int)]
@@ -167,7 +169,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "mvx_version", "mvx_last_error", "mvx_workspace_bytes", "mvx_host_staging_bytes", "mvx_voxelize",
     "mvx_voxelize_host", "mvx_check_status", "mvx_launches_per_call", "mvx_voxelize_form", "mvx_profile_begin",
-    "mvx_profile_end", "mvx_random_transforms", "mvx_synth_ligands",
+    "mvx_profile_end", "mvx_random_transforms", "mvx_synth_ligands", "mvx_compact_bricks",
 ]
 
 

@@ -523,6 +523,31 @@ int mvx_synth_ligands(uint64_t seed, uint64_t first_mol, int32_t num_mols, int32
     return MVX_OK;
 }
 
+int mvx_compact_bricks(const mvx_grid_spec* spec, const mvx_batch* batch, const void* grids, const void* workspace,
+                       uint32_t* brick_ids, float* brick_vals, uint32_t capacity, uint32_t* count, void* stream) {
+    Plan pl;
+    int rc = make_plan(spec, batch, &pl);
+    if (rc != MVX_OK) return rc;
+    if (batch->out_dtype != MVX_OUT_F32) return fail(MVX_ERR_UNSUPPORTED, "brick compaction needs float32 grids");
+    if (!count) return fail(MVX_ERR_NULL_POINTER, "count is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    MVX_CUDA_OK(cudaMemsetAsync(count, 0, sizeof(uint32_t), st));
+    if (batch->num_mols == 0) return MVX_OK;
+    if (!grids || (capacity > 0 && (!brick_ids || !brick_vals))) return fail(MVX_ERR_NULL_POINTER, "grids / brick buffers");
+    if ((uintptr_t)grids % 16 != 0 || (uintptr_t)brick_vals % 16 != 0) return fail(MVX_ERR_BAD_SHAPE, "grids and brick_vals must be 16-byte aligned");
+    mvx::CompactParams cp;
+    cp.dim = spec->dimension; cp.ncx = pl.geo.ncx; cp.ncol = pl.ncol; cp.Cout = batch->out_channels;
+    cp.nbz = (spec->dimension + mvx::kBrick - 1) / mvx::kBrick; cp.B = batch->num_mols;
+    cp.bins = workspace ? (const uint2*)((const char*)workspace + pl.off_bins) : nullptr;
+    cp.grid = (const float*)grids; cp.ids = brick_ids; cp.vals = brick_vals; cp.cap = capacity; cp.count = count;
+    const unsigned long long nblk = (unsigned long long)batch->num_mols * pl.ncol;
+    const unsigned long long nbricks = nblk * cp.Cout * cp.nbz;
+    if (nblk > 0x7fffffffULL || nbricks > 0xffffffffULL) return fail(MVX_ERR_BAD_SHAPE, "batch too large for one launch; split it");
+    mvx::mvx_compact_bricks_kernel<<<(unsigned)nblk, 256, 0, st>>>(cp);
+    MVX_CUDA_OK(cudaGetLastError());
+    return MVX_OK;
+}
+
 int mvx_profile_begin(int max_calls) {
     if (g_prof.active) return fail(MVX_ERR_UNSUPPORTED, "a profile is already open on this thread");
     if (max_calls < 1) return fail(MVX_ERR_BAD_SHAPE, "max_calls must be >= 1");

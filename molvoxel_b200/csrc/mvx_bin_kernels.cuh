@@ -697,6 +697,68 @@ __global__ void __launch_bounds__(128) mvx_synth_ligands_kernel(const SynthParam
 }
 
 // ---------------------------------------------------------------------------------------------
+// Brick compaction (host-side consumers): a finished fp32 grid is >= 97 % zeros for ligands, so copying it to the host
+// densely measures PCIe.  One CTA per (molecule, 8x8 column) — empty columns are known from the binning pass and exit
+// at once —, one warp per (channel, 8-voxel z range): a brick of 8 x 8 x 8 voxels (2 KB) that holds any non-zero
+// value claims a slot of the compact buffer (atomic counter; slot order is arbitrary, the id says where the brick
+// belongs) and is copied there.  Bricks that stick out of the grid (D % 8 != 0) are zero-padded.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBrick = 8;
+struct CompactParams {
+    int dim, ncx, ncol, Cout, nbz, B;
+    const uint2* bins;      // per (molecule, column): count in .y (nullptr: scan every column)
+    const float* grid;      // (B, Cout, D, D, D)
+    uint32_t* ids;          // (cap) brick id = ((mol * Cout + c) * ncol + col) * nbz + bz
+    float* vals;            // (cap, 512), brick-local [x][y][z]
+    uint32_t cap;
+    uint32_t* count;        // bricks found (may exceed cap: the caller re-runs with a larger buffer)
+};
+
+__global__ void __launch_bounds__(256) mvx_compact_bricks_kernel(const CompactParams P) {
+    const int col = blockIdx.x % P.ncol, mol = blockIdx.x / P.ncol;
+    if (P.bins != nullptr && P.bins[(size_t)mol * P.ncol + col].y == 0u) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = P.dim;
+    const int x0 = (col / P.ncx) * kBrick, y0 = (col % P.ncx) * kBrick;
+    const size_t plane = (size_t)D * D * D;
+    const bool vec = (D & 3) == 0;
+    for (int b = warp; b < P.Cout * P.nbz; b += 8) {
+        const int c = b / P.nbz, bz = b - c * P.nbz;
+        const int z0 = bz * kBrick;
+        const float* g = P.grid + ((size_t)mol * P.Cout + c) * plane;
+        float4 v[4];   // lane owns rows 2 * lane, 2 * lane + 1 (row = (x, y), 8 voxels of z)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int row = 2 * lane + r, x = x0 + (row >> 3), y = y0 + (row & 7);
+            const float* src = g + ((size_t)x * D + y) * D + z0;
+            const bool in = x < D && y < D;
+            if (vec) {
+                v[2 * r] = (in && z0 < D) ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[2 * r + 1] = (in && z0 + 4 < D) ? __ldg(reinterpret_cast<const float4*>(src) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                float t[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t[k] = (in && z0 + k < D) ? __ldg(src + k) : 0.f;
+                v[2 * r] = make_float4(t[0], t[1], t[2], t[3]);
+                v[2 * r + 1] = make_float4(t[4], t[5], t[6], t[7]);
+            }
+        }
+        bool nz = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) nz = nz || v[q].x != 0.f || v[q].y != 0.f || v[q].z != 0.f || v[q].w != 0.f;
+        if (__ballot_sync(0xffffffffu, nz) == 0u) continue;
+        uint32_t slot = 0u;
+        if (lane == 0) slot = atomicAdd(P.count, 1u);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= P.cap) continue;
+        if (lane == 0) P.ids[slot] = (uint32_t)((((size_t)mol * P.Cout + c) * P.ncol + col) * P.nbz + bz);
+        float4* dst = reinterpret_cast<float4*>(P.vals + (size_t)slot * 512) + 4 * lane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) __stcs(dst + q, v[q]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // voxelize, precision = 64 (the reference's `precision=64` constructor argument, numpy/voxelizer.py:28-34; SURVEY
 // row f4): distances, dr = dist / r, the Gaussian and the accumulation all in fp64, (B, Cout, D, D, D) float64 out.
 // API completeness, not a tuned path: one CTA per (molecule, 8x8 column) on the column lists of the generic form,

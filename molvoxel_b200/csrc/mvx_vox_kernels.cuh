@@ -728,18 +728,20 @@ __device__ __forceinline__ void tiles_body(const VoxParams& P, const int tile_id
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) off[k] = row_off || dzf == k;
                             }
-                            // r^2 - tau <= s <= r^2 + tau for any of the 4 voxels -> replay in fp64.  Two direct compares
-                            // per voxel: a |s - r^2| <= tau form loses voxels whose s rounds onto the band's lower edge
-                            // (the midpoint and half-width of two fp32 numbers next to 1.0 carry 0.2 % of rounding error)
-                            float sk[4], w[4];
-                            bool band = false;
+                            // trigger: |s - r^2| <= tau, WIDENED, for any of the 4 voxels -> those voxels replay in fp64.  The
+                            // midpoint and half-width of r^2 +- tau are fp32 results with up to 4e-7 * r^2 of rounding error
+                            // (0.2 % of tau next to 1.0): the margin below covers it, so no s in [r^2 - tau, r^2 + tau] slips
+                            // through; the decision proper is the pair of direct compares inside
+                            const float r2c = 0.5f * (A.w + Bv.x), tauh = fmaf(4e-7f, r2c, 0.505f * (A.w - Bv.x));
+                            float sk[4], w[4], dmin = 3.0e38f;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const float dz = A.z - oz[k];
                                 sk[k] = fmaf(dz, dz, dxy);
                                 w[k] = (sk[k] < Bv.x && !off[k]) ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
-                                band = band || (sk[k] >= Bv.x && sk[k] <= A.w);
+                                dmin = fminf(dmin, fabsf(sk[k] - r2c));
                             }
+                            const bool band = dmin <= tauh;
                             const float4* ent = sE + (int)wI[j] * ES4;
                             if (band) {   // rare
                                 const int n = (int)__float_as_uint(ent[2].x);
@@ -1175,17 +1177,18 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
                             const float4 Bv = lds128(eb + 16u);
                             const float dx = A.x - ox, dy = A.y - oy;
                             const float dxy = fmaf(dx, dx, dy * dy);
-                            // r^2 - tau <= s <= r^2 + tau for any of the 4 voxels -> replay in fp64 (two direct compares
-                            // per voxel: see the tile form)
-                            float sk[4], w[4];
-                            bool band = false;
+                            // trigger: |s - r^2| <= tau, widened by the rounding error of the fp32 midpoint / half-width
+                            // (see the tile form), for any of the 4 voxels -> those voxels replay in fp64
+                            const float r2c = 0.5f * (A.w + Bv.x), tauh = fmaf(4e-7f, r2c, 0.505f * (A.w - Bv.x));
+                            float sk[4], w[4], dmin = 3.0e38f;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const float dz = A.z - oz[k];
                                 sk[k] = fmaf(dz, dz, dxy);
                                 w[k] = (sk[k] < Bv.x) ? (BINARY ? 1.0f : fast_exp2(sk[k] * Bv.y)) : 0.f;
-                                band = band || (sk[k] >= Bv.x && sk[k] <= A.w);
+                                dmin = fminf(dmin, fabsf(sk[k] - r2c));
                             }
+                            const bool band = dmin <= tauh;
                             const uint32_t forb = __float_as_uint(Bv.z);
                             if (band || forb != kNoForb) {   // rare: tolerance band, or a block-cull plane in reach
                                 bool off[4];

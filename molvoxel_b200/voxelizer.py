@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .sparse import SparseGrids
 from .transform import RandomTransform, host_transform_rows, transform_rows
 
 
@@ -565,11 +566,56 @@ class Voxelizer:
             rc = fn(ctypes.byref(spec), ctypes.byref(b), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws_ptr),
                     ctypes.c_size_t(ws_bytes), stream)
         _lib.raise_for_status(rc)
+        # shapes / flags of this call (pointers are not dereferenced again): compact() finds the column occupancy the
+        # binning pass left in the workspace
+        last = _lib.Batch()
+        ctypes.memmove(ctypes.byref(last), ctypes.byref(b), ctypes.sizeof(b))
+        self._last_call = (spec, last, ws_ptr, out.data_ptr())
         if on_device:
             for t in keep:   # inputs converted on the fly must outlive the asynchronous kernels
                 if isinstance(t, torch.Tensor):
                     t.record_stream(torch.cuda.current_stream(self.device))
         return out
+
+    # ---- brick-sparse grids for host-side consumers (molvoxel_b200/sparse.py) ----
+    def compact_into(self, grids: torch.Tensor, ids: torch.Tensor, vals: torch.Tensor, count: torch.Tensor):
+        """Enqueue the brick compaction of `grids` (the output of the LAST forward_* call of this voxelizer, float32) on
+        the current stream, no synchronisation: non-empty 8x8x8 bricks -> vals (cap, 512) float32 / ids (cap,) int32,
+        their number -> count (1,) int32 (it may exceed the capacity: the surplus was dropped)."""
+        assert self.out_dtype == torch.float32 and grids.dtype == torch.float32 and grids.is_contiguous(), "compact needs float32 grids"
+        assert getattr(self, "_last_call", None) is not None, "compact() follows a forward_* call"
+        spec, last, ws_ptr, out_ptr = self._last_call
+        use_ws = out_ptr == grids.data_ptr() and int(last.num_mols) == int(grids.shape[0])
+        if not use_ws:   # any other grid of this voxelizer's geometry: scan every column
+            last = _lib.Batch()
+            ctypes.memmove(ctypes.byref(last), ctypes.byref(self._last_call[1]), ctypes.sizeof(last))
+            last.num_mols, last.out_channels = int(grids.shape[0]), int(grids.shape[1])
+            last.num_channels = min(int(last.num_channels), int(grids.shape[1]))
+        cap = min(int(ids.shape[0]), int(vals.shape[0]))
+        with torch.cuda.device(self.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            rc = _lib.lib().mvx_compact_bricks(ctypes.byref(spec), ctypes.byref(last), ctypes.c_void_p(grids.data_ptr()),
+                                               ctypes.c_void_p(ws_ptr if use_ws else 0), ctypes.c_void_p(ids.data_ptr()),
+                                               ctypes.c_void_p(vals.data_ptr()), ctypes.c_uint32(cap),
+                                               ctypes.c_void_p(count.data_ptr()), stream)
+        _lib.raise_for_status(rc)
+
+    def compact(self, grids: torch.Tensor, capacity: int | None = None) -> SparseGrids:
+        """Brick-sparse form of the grids of the last forward_* call (synchronises once to learn the brick count;
+        grows the buffers and repeats if `capacity` was too small)."""
+        B, C, D = int(grids.shape[0]), int(grids.shape[1]), self._dimension
+        nb = -(-D // 8)
+        total = B * C * nb ** 3
+        cap = int(capacity) if capacity else max(1024, total // 8)
+        while True:
+            ids = torch.empty(cap, dtype=torch.int32, device=self.device)
+            vals = torch.empty((cap, 512), dtype=torch.float32, device=self.device)
+            count = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.compact_into(grids, ids, vals, count)
+            n = int(count.item())
+            if n <= cap:
+                return SparseGrids(ids[:n], vals[:n], (B, C, D))
+            cap = n
 
     def check_status(self):
         """Synchronise and raise if the last device-path call flagged bad types / radii (device-side validation)."""
