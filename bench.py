@@ -399,10 +399,22 @@ class Chunks:
                 self.host.append(dict(coords=coords_h[a0:a1], offs=pin(self.offs_chunks_h[i]), centers=centers_h[:m1 - m0],
                                       chan=types_h[a0:a1], radii=1.0))
         else:
+            # the loader's job: per-molecule point clouds -> pinned CSR batch.  compact=True picks the
+            # lossless small encodings by itself (uint8 rows for 0/1 features, float32 for fp32-representable coordinates
+            # next to float64 centres); dense float features / fp64-only coordinates stay as they are.
+            from molvoxel_b200.pointcloud import Collator, PointCloud
+            self.host_plain = []
             for b in self.batches:
-                ch = b["types"] if self.w["mode"] == "types" else b["feats"]
-                self.host.append(dict(coords=pin(b["coords"]), offs=pin(b["offs"]), centers=pin(b["centers"]), chan=pin(ch),
-                                      radii=b["radii"] if np.isscalar(b["radii"]) else pin(b["radii"])))
+                chn = b["types"] if self.w["mode"] == "types" else b["feats"]
+                offs = b["offs"]
+                clouds = [PointCloud(b["coords"][offs[m]:offs[m + 1]], chn[offs[m]:offs[m + 1]], self.w["C"]) for m in range(self.B)]
+                rad = None if np.isscalar(b["radii"]) else [b["radii"][offs[m]:offs[m + 1]] for m in range(self.B)]
+                for compact, dst in ((True, self.host), (False, self.host_plain)):
+                    col = Collator(pinned=True, compact=compact)
+                    self.keep.append(col)
+                    c = col(clouds, centers=b["centers"], radii=rad)
+                    dst.append(dict(coords=c["coords"], offs=c["mol_offsets"], centers=c["centers"], chan=c["channels"],
+                                    radii=b["radii"] if np.isscalar(b["radii"]) else c["radii"]))
 
     def host_args(self, i):
         return self.host[i]
@@ -530,8 +542,8 @@ def run_b200_arm(args):
 
     # ---- extras (reported, never fail the bench) --------------------------------------------------------
     extras = {}
-    if w["mode"] == "features" and not ch.sweep:
-        extras["compact_features"] = compact_features_leg(ch, vox, fwd, ring, timed, steps, warm_steps, world, K, n_calls)
+    if not ch.sweep:
+        extras["plain_inputs"] = plain_inputs_leg(ch, vox, fwd, ring, timed, steps, warm_steps, world, K, n_calls)
     extras["with_grid_d2h"] = grid_d2h_leg(ch, vox, fwd, ring, esize, C, D, out_dt, world, dev)
     if esize == 4:
         extras["with_grid_d2h_sparse"] = grid_d2h_sparse_leg(ch, vox, fwd, ring, C, D, world, dev)
@@ -578,7 +590,8 @@ def run_b200_arm(args):
         "timed_region_s": ms_total * 1e-3, "molecules_timed": int(mols_all),
         "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(4 * n_calls / K),
                 "ms_per_step": ms_e2e / K, "blocking_value": mols_all / (ms_e2e_blocking * 1e-3), **extras,
-                "note": "public Voxelizer.forward_*_batch with pinned HOST inputs, every call: async H2D (copy stream, 2-deep staging ring) -> prep/bin/voxelize -> D2H of the status word; one sync at the end of the timed region. blocking_value = mvx_voxelize_host (one sync per call). Grids stay in HBM (reference torch-backend convention); with_grid_d2h* = grids delivered to host memory"},
+                "input_encoding": {k: str(v.dtype) for k, v in ch.host_args(0).items() if isinstance(v, np.ndarray)},
+                "note": "public API with pinned HOST inputs (pool workloads: collated by molvoxel_b200.Collator(pinned=True, compact=True), which narrows losslessly where it can), every call: Voxelizer.forward_*_batch(non_blocking=True) = async H2D (copy stream, 2-deep staging ring) -> prep/bin/voxelize -> D2H of the status word; one sync at the end of the timed region. blocking_value = mvx_voxelize_host (one sync per call). Grids stay in HBM (reference torch-backend convention); with_grid_d2h* = grids delivered to host memory"},
         "gpu_launches": per_call * n_calls,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(name), "kernel": kernel_name, "kernel_ms": prof["vox"],
@@ -602,32 +615,21 @@ def run_b200_arm(args):
         dist.destroy_process_group()
 
 
-def compact_features_leg(ch, vox, fwd, ring, timed, steps, warm_steps, world, K, n_calls):
-    """Feature rows that are exactly representable in uint8 (one-hot / flag features, cfg2) and fp32-representable
-    coordinates cross PCIe compact (mvx_batch.features_dtype, fp32 coords + fp64 centres): the same grids."""
-    import torch
+def plain_inputs_leg(ch, vox, fwd, ring, timed, steps, warm_steps, world, K, n_calls):
+    """The same e2e path with the host batches collated WITHOUT the lossless compaction (float64 coordinates, float32
+    feature rows): what `e2e` was before the loader learned to pick the small encodings.  Identical grids."""
     try:
-        if not all(bool((h["chan"] == h["chan"].astype(np.uint8)).all()) for h in ch.host):
-            return None
-        compact, keep = [], []
-        for h in ch.host:
-            c32 = h["coords"].astype(np.float32)
-            if not np.array_equal(c32.astype(np.float64), h["coords"]):
-                c32 = h["coords"]
-            d = dict(h)
-            for key, arr in (("coords", c32), ("chan", h["chan"].astype(np.uint8))):
-                t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
-                keep.append(t)
-                d[key] = t.numpy()
-            compact.append(d)
+        same = all(h["chan"].dtype == p["chan"].dtype and h["coords"].dtype == p["coords"].dtype for h, p in zip(ch.host, ch.host_plain))
+        if same:
+            return {"note": "the collator found nothing to narrow for this workload; e2e already uses these inputs"}
 
         def call(i, k):
-            fwd(compact[i], out=ring[k & 1][:ch.mols(i)], max_radius=ch.max_r, rng_offset=ch.first_mol(i), non_blocking=True)
+            fwd(ch.host_plain[i], out=ring[k & 1][:ch.mols(i)], max_radius=ch.max_r, rng_offset=ch.first_mol(i), non_blocking=True)
         ms, _, _ = timed(call, steps, warm_steps)
         vox.check_status()
-        nbytes = float(np.mean([sum(int(v.nbytes) for v in c.values() if isinstance(v, np.ndarray)) for c in compact]))
+        nbytes = float(np.mean([sum(int(v.nbytes) for v in c.values() if isinstance(v, np.ndarray)) for c in ch.host_plain]))
         return {"value": world * sum(ch.mols(i) for s in steps for i in s) / (ms * 1e-3), "h2d_bytes_per_step": int(nbytes * n_calls / K),
-                "note": "e2e with the (0/1-valued) feature rows as uint8 and the fp32-representable coordinates as float32 host arrays (centres fp64, so numpy's promotion gives the same fp64 arithmetic): identical grids, a third of the bytes"}
+                "note": "float64 coordinates + float32 feature rows over PCIe (Collator(compact=False))"}
     except Exception as e:
         return {"error": repr(e)[:200]}
 

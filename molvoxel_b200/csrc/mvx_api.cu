@@ -250,8 +250,9 @@ cudaError_t launch_density(const mvx::VoxParams& vp, bool binary, int form, int 
 
 // column groups per molecule for the bin pass: 1 (fused kernel) once the batch alone gives two waves of
 // CTAs on the 148 SMs, otherwise enough groups to get there (at least 8 columns = one per warp each).
-int bin_groups(int B, int ncol) {
+int bin_groups(int B, int ncol, long long N = -1) {
     if (B >= 296) return 1;
+    if (N >= 0 && N <= 512) return 1;   // a few small molecules (the one-ligand-per-call pattern): latency, one launch
     int g = (1184 + B - 1) / (B > 0 ? B : 1);   // aim at ~8 CTAs per SM so the latency-bound scans overlap
     int gmax = (ncol + 7) / 8;
     if (g > gmax) g = gmax;
@@ -315,8 +316,8 @@ int mvx_launches_per_call(const mvx_grid_spec* spec, const mvx_batch* batch) {
     if (batch->num_mols == 0) return 0;
     const bool chan_feat = batch->mode == MVX_MODE_FEATURES && spec->radii_type == MVX_RADII_CHANNEL_WISE;
     int nvox = (chan_feat && batch->out_dtype != MVX_OUT_F64) ? batch->num_channels : 1;
-    const int nbin = layered(pl.form) ? (batch->total_atoms > 0 ? 3 : 1) : (bin_groups(batch->num_mols, pl.ncol) <= 1 ? 1 : 2);   // scan, place, build
-    const int nexp = (pl.form == FORM_CELLS && batch->total_atoms > 0 && bin_groups(batch->num_mols, pl.ncol) > 1) ? 1 : 0;   // fused into bin for big batches
+    const int nbin = layered(pl.form) ? (batch->total_atoms > 0 ? 3 : 1) : (bin_groups(batch->num_mols, pl.ncol, batch->total_atoms) <= 1 ? 1 : 2);   // scan, place, build
+    const int nexp = (pl.form == FORM_CELLS && batch->total_atoms > 0 && bin_groups(batch->num_mols, pl.ncol, batch->total_atoms) > 1) ? 1 : 0;   // fused into bin for big batches
     const int nwide = (batch->mode == MVX_MODE_FEATURES && batch->features_dtype != MVX_F32 && batch->total_atoms > 0) ? 1 : 0;
     return (batch->total_atoms > 0 ? 1 : 0) + nwide + nbin + nexp + nvox * (pl.form == FORM_PIPE ? 2 : 1);   // prep + bin + expand + voxelize
 }
@@ -420,7 +421,7 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         bp.B = B; bp.ncol = pl.ncol; bp.ncx = pl.geo.ncx; bp.maxcols = pl.maxcols;
         bp.mol_offsets = batch->mol_offsets; bp.colrange = colrange; bp.bins = bins; bp.lists = lists;
         const size_t smem = 2 * (size_t)pl.ncol * sizeof(uint32_t);
-        const int groups = bin_groups(B, pl.ncol);
+        const int groups = bin_groups(B, pl.ncol, N);
         mvx::ExpandParams ep;   // column lists -> staged-ready entries (CELLS form)
         ep.res = pl.geo.res; ep.half_width = pl.geo.half_width; ep.sigma = spec->sigma;
         ep.tau_lin = pl.tau_lin; ep.tau_quad = pl.tau_quad;
@@ -581,11 +582,27 @@ int mvx_profile_end(double* ms_prep, double* ms_bin, double* ms_voxelize, int* n
     return MVX_OK;
 }
 
+namespace {
+// one pinned word per calling thread for the status read-back (a pageable destination makes the copy a staged,
+// synchronous driver round trip)
+struct PinnedWord {
+    int* p = nullptr;
+    int* get() {
+        if (p == nullptr && cudaHostAlloc((void**)&p, sizeof(int), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); p = nullptr; }
+        return p;
+    }
+    ~PinnedWord() { if (p != nullptr) cudaFreeHost(p); }
+};
+}  // namespace
+
 int mvx_check_status(void* workspace, void* stream) {
     if (!workspace) return fail(MVX_ERR_NULL_POINTER, "workspace is NULL");
-    int flags = 0;
-    MVX_CUDA_OK(cudaMemcpyAsync(&flags, workspace, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    thread_local PinnedWord pw;
+    int pageable = 0;
+    int* dst = pw.get() != nullptr ? pw.get() : &pageable;
+    MVX_CUDA_OK(cudaMemcpyAsync(dst, workspace, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     MVX_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    const int flags = *dst;
     if (flags & mvx::kFlagBadType) return fail(MVX_ERR_DEVICE_FLAG, "a type index is outside [0, num_channels)");
     if (flags & mvx::kFlagRadiusOverMax) return fail(MVX_ERR_DEVICE_FLAG, "a radius exceeds max_radius");
     return MVX_OK;

@@ -115,12 +115,26 @@ def from_rdkit(rdmol, symbols, bondtypes=None, unknown=False):
 class Collator:
     """Packs point clouds into the CSR batch of Voxelizer.forward_*_batch.  With pinned=True the arrays are
     views of reusable page-locked buffers (two sets, used alternately, so a batch can be filled while the
-    previous one is still being copied)."""
+    previous one is still being copied).  A set is handed out again only after the copy that last read it has
+    finished: pass the event of that copy (`Voxelizer.last_copy_event` after a non_blocking forward) to `in_flight()`.
 
-    def __init__(self, pinned: bool = False):
+    compact=True sends fewer bytes over PCIe where that is LOSSLESS: feature rows whose values are all exactly
+    representable as uint8 (one-hot / flag / count features) are packed as uint8 (widened exactly on the device,
+    mvx_batch.features_dtype), and coordinates that are exactly representable in float32 are packed as float32 when
+    centres are given as float64 — numpy's promotion then still centres in fp64 (reference numpy/voxelizer.py:263),
+    so the grids are bit-identical.  The checks run here, in the loader, where the data is touched anyway."""
+
+    def __init__(self, pinned: bool = False, compact: bool = False):
         self.pinned = pinned
+        self.compact = compact
         self._bufs = [{}, {}]
+        self._events = [None, None]
         self._turn = 0
+
+    def in_flight(self, event):
+        """The set returned by the last call is being read by an asynchronous copy that `event` (a torch.cuda.Event
+        recorded after it) completes; the set is not refilled before that."""
+        self._events[self._turn ^ 1] = event
 
     def _array(self, name, shape, dtype):
         n = int(np.prod(shape))
@@ -128,11 +142,11 @@ class Collator:
             return np.empty(shape, dtype=dtype)
         import torch
         slot = self._bufs[self._turn]
-        buf = slot.get(name)
+        buf = slot.get((name, np.dtype(dtype).str))
         tdt = torch.from_numpy(np.empty(0, dtype=dtype)).dtype
-        if buf is None or buf.dtype != tdt or buf.numel() < n:
+        if buf is None or buf.numel() < n:
             buf = torch.empty(max(n, 1) * 5 // 4 + 16, dtype=tdt).pin_memory()
-            slot[name] = buf
+            slot[(name, np.dtype(dtype).str)] = buf
         return buf[:n].view(*shape).numpy()
 
     def __call__(self, clouds, centers=None, radii=None):
@@ -140,15 +154,24 @@ class Collator:
         every cloud, fp64) or (B, 3).  radii: None, or per-cloud (P_i,) arrays (atom-wise radii).
         Returns dict(coords, mol_offsets, centers, channels, radii, num_channels)."""
         B = len(clouds)
+        if self._events[self._turn] is not None:   # the copy that last read this set of pinned buffers has finished
+            self._events[self._turn].synchronize()
+            self._events[self._turn] = None
         counts = np.array([c.coords.shape[0] for c in clouds], dtype=np.int64)
         offs = self._array("offs", (B + 1,), np.int32)
         offs[0] = 0
         np.cumsum(counts, out=offs[1:])
         N = int(offs[-1])
-        coords = self._array("coords", (N, 3), np.float64)
         is_types = B == 0 or clouds[0].channels.ndim == 1
         C = clouds[0].num_channels if B else 0
-        channels = self._array("chan", (N,) if is_types else (N, C), np.int32 if is_types else np.float32)
+        cdt, fdt = np.float64, np.float32
+        if self.compact and B:
+            if centers is not None and all(np.array_equal(c.coords, np.asarray(c.coords, dtype=np.float32)) for c in clouds):
+                cdt = np.float32
+            if not is_types and all(np.array_equal(c.channels, np.asarray(c.channels).astype(np.uint8)) for c in clouds):
+                fdt = np.uint8
+        coords = self._array("coords", (N, 3), cdt)
+        channels = self._array("chan", (N,) if is_types else (N, C), np.int32 if is_types else fdt)
         for c, a, b in zip(clouds, offs[:-1], offs[1:]):
             assert c.num_channels == C and (c.channels.ndim == 1) == is_types, "point clouds of one batch must agree in channels"
             coords[a:b] = c.coords
@@ -157,8 +180,8 @@ class Collator:
         if isinstance(centers, str):
             assert centers == "mean"
             cen = self._array("centers", (B, 3), np.float64)
-            for m, (a, b) in enumerate(zip(offs[:-1], offs[1:])):
-                cen[m] = coords[a:b].mean(axis=0) if b > a else 0.0
+            for m, (c, a, b) in enumerate(zip(clouds, offs[:-1], offs[1:])):
+                cen[m] = np.asarray(c.coords, dtype=np.float64).mean(axis=0) if b > a else 0.0
             out["centers"] = cen
         elif centers is not None:
             cen = self._array("centers", (B, 3), np.float64)

@@ -90,7 +90,9 @@ class Voxelizer:
         # (numpy/transform.py:56-59); translate_once=True gives the torch backend's single addition
         self.translate_once = bool(kwargs.get("translate_once", False))
         self._ws = None
+        self._ws_need = {}
         self._pipe = None
+        self.last_copy_event = None
         self._sticky_flags = 0
         _lib.lib()   # fail loudly here if the CUDA library cannot be built/loaded
 
@@ -361,6 +363,7 @@ class Voxelizer:
                 outs.append(dst)
             slot["copied"].record(pipe["copy"])
         cur.wait_event(slot["copied"])
+        self.last_copy_event = slot["copied"]   # host buffers of this call may be refilled once it has completed
         return outs, slot
 
     def _forward_batch(self, mode, coords, mol_offsets, centers, channels, radii, C, random_translation,
@@ -550,21 +553,35 @@ class Voxelizer:
 
         L = _lib.lib()
         spec = self._spec()
-        need = ctypes.c_size_t(0)
-        _lib.raise_for_status(L.mvx_workspace_bytes(ctypes.byref(spec), ctypes.byref(b), ctypes.byref(need)))
-        total = need.value
-        if not on_device:
-            stg = ctypes.c_size_t(0)
-            _lib.raise_for_status(L.mvx_host_staging_bytes(ctypes.byref(spec), ctypes.byref(b), ctypes.byref(stg)))
-            total += stg.value
+        # workspace size of this call shape: cached (two C calls, each planning the batch, per forward otherwise)
+        key = (mode, B, N, C, out_channels, on_device, int(b.coords_dtype), int(b.centers_dtype), int(b.features_dtype),
+               int(b.out_dtype), float(b.radius), float(b.max_radius), int(b.transform_flags), tf_rows is not None,
+               centers is None, self._radii_type, self._density_type, self.blockdim, float(self._sigma))
+        total = self._ws_need.get(key)
+        if total is None:
+            need = ctypes.c_size_t(0)
+            _lib.raise_for_status(L.mvx_workspace_bytes(ctypes.byref(spec), ctypes.byref(b), ctypes.byref(need)))
+            total = need.value
+            if not on_device:
+                stg = ctypes.c_size_t(0)
+                _lib.raise_for_status(L.mvx_host_staging_bytes(ctypes.byref(spec), ctypes.byref(b), ctypes.byref(stg)))
+                total += stg.value
+            if len(self._ws_need) > 256:
+                self._ws_need.clear()
+            self._ws_need[key] = total
         ws = self._workspace(total)
         ws_ptr = (ws.data_ptr() + 255) // 256 * 256
         ws_bytes = ws.numel() - (ws_ptr - ws.data_ptr())
-        with torch.cuda.device(self.device):
+        fn = L.mvx_voxelize if on_device else L.mvx_voxelize_host
+        if torch.cuda.current_device() == self.device.index:
             stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-            fn = L.mvx_voxelize if on_device else L.mvx_voxelize_host
             rc = fn(ctypes.byref(spec), ctypes.byref(b), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws_ptr),
                     ctypes.c_size_t(ws_bytes), stream)
+        else:
+            with torch.cuda.device(self.device):
+                stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+                rc = fn(ctypes.byref(spec), ctypes.byref(b), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws_ptr),
+                        ctypes.c_size_t(ws_bytes), stream)
         _lib.raise_for_status(rc)
         # shapes / flags of this call (pointers are not dereferenced again): compact() finds the column occupancy the
         # binning pass left in the workspace

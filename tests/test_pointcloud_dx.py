@@ -113,6 +113,28 @@ def test_collate_builds_the_csr_batch():
     assert fb["channels"].shape == (10, 3) and fb["channels"].dtype == np.float32 and fb["radii"] is None
 
 
+def test_compact_collation_is_lossless_or_declined():
+    """Collator(compact=True): uint8 feature rows only when every value is exactly a uint8, float32 coordinates only when
+    they are fp32-representable AND fp64 centres are given (numpy then still centres in fp64); otherwise nothing narrows."""
+    rng = np.random.default_rng(8)
+    mols = [_random_mol(rng, n, 0, 5, 0) for n in (7, 9)]
+    for m in mols:
+        m["atom_coords"] = m["atom_coords"].astype(np.float32).astype(np.float64)
+    feats = [mol_point_cloud(channel_type="features", **m) for m in mols]        # one-hot rows: exact in uint8
+    col = Collator(compact=True)
+    b = col(feats, centers="mean")
+    assert b["channels"].dtype == np.uint8 and b["coords"].dtype == np.float32 and b["centers"].dtype == np.float64
+    plain = Collator()(feats, centers="mean")
+    assert np.array_equal(b["channels"].astype(np.float32), plain["channels"]) and np.array_equal(b["coords"].astype(np.float64), plain["coords"])
+    assert np.array_equal(b["centers"], plain["centers"])
+    assert col(feats, centers=None)["coords"].dtype == np.float64                  # no centre: the dtype is semantics
+    mols[0]["atom_coords"] = mols[0]["atom_coords"] + 1e-9                          # not fp32-representable any more
+    feats2 = [mol_point_cloud(channel_type="features", **m) for m in mols]
+    assert col(feats2, centers="mean")["coords"].dtype == np.float64
+    feats2[1].channels[0, 0] = 0.5                                                  # not a uint8 any more
+    assert col(feats2, centers="mean")["channels"].dtype == np.float32
+
+
 def test_dx_writer_is_byte_identical_to_the_reference_writer(tmp_path):
     vals = np.load(os.path.join(GOLDEN, "dx_small_values.npy"))
     p = tmp_path / "out.dx"

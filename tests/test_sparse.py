@@ -55,7 +55,8 @@ def test_compaction_is_lossless_and_minimal(D, res):
     order = np.argsort(host.ids.astype(np.int64) & 0xFFFFFFFF)
     assert np.array_equal((host.ids.astype(np.int64) & 0xFFFFFFFF)[order], want_ids)
     assert np.array_equal(host.vals[order], want_vals)
-    assert sp.nbytes < 0.2 * dense.nbytes
+    if D == 64:   # a ligand in a 32 A box: a few per cent of the bricks
+        assert sp.nbytes < 0.1 * dense.nbytes
     # a too small capacity is detected and the buffers grow
     assert vox.compact(out, capacity=7).num_bricks == sp.num_bricks
     # a grid that is not the last call's output (no column occupancy to lean on): every column is scanned
