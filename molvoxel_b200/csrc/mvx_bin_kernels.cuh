@@ -443,8 +443,11 @@ __global__ void __launch_bounds__(256) mvx_lscan_kernel(const LBinParams P, cons
                     e[k] = __shfl_sync(0xffffffffu, my_off + my_cnt, min(L0 + min(k, ncz - 1), 31)) - o0;
                 if (lane == 0) {
                     TileDesc d;
-                    d.start = (unsigned long long)lseg + s_off[col] + o0; d.total = e[3];
-                    d.lend[0] = e[0]; d.lend[1] = e[1]; d.lend[2] = e[2]; d.lend[3] = e[3]; d.pad = 0u;
+                    d.start = (unsigned long long)lseg + s_off[col] + o0; d.total = e[3]; d.mol = (uint32_t)mol;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) d.lend[k] = (uint16_t)min(e[k], 65535u);
+                    d.origin = (uint32_t)((col / P.ncx) * kTile) | ((uint32_t)((col % P.ncx) * kTile) << 10) | ((uint32_t)(zc * P.tz) << 20);
+                    d.pad = 0u;
                     P.tdesc[gcol * P.nzc + zc] = d;
                 }
             }

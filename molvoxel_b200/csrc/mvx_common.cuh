@@ -101,12 +101,16 @@ struct __align__(16) ColEntry {
 };
 static_assert(sizeof(ColEntry) == 48, "ColEntry layout");
 
-// One tile (8 x 8 x tz voxels of one molecule) as the pipelined kernel's producer sees it: where its layered
-// entries start, how many there are, and where each 16-voxel z layer ends.  32 bytes, fetched by one bulk copy.
+// One tile (8 x 8 x tz voxels of one molecule) as the pipelined kernel sees it: where its layered entries start, how
+// many there are, where each 16-voxel z layer ends, and which voxels it covers (so that no warp has to take the tile
+// index apart with integer divisions).  32 bytes, fetched by one bulk copy.
 struct __align__(16) TileDesc {
     unsigned long long start;   // first layered entry of the tile (index into lent, in entries)
     uint32_t total;             // entries of the tile (the layers of a z chunk are consecutive)
-    uint32_t lend[4];           // end of layer k relative to start (tz <= 64: at most 4 layers)
+    uint32_t mol;               // molecule
+    uint16_t lend[4];           // end of layer k relative to start (tz <= 64: at most 4 layers); saturates at 65535 —
+                                // such tiles exceed what the pipelined form takes and go to the tile form, which does not read it
+    uint32_t origin;            // first voxel: x0 | y0 << 10 | z0 << 20
     uint32_t pad;
 };
 static_assert(sizeof(TileDesc) == 32, "TileDesc layout");

@@ -1045,13 +1045,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
         mbar_wait(&dfull[s], (it / ND) & 1u);
         const uint32_t total = sDesc[s].total;
 
+        // which voxels the tile covers comes with its descriptor (no integer divisions per warp and tile)
+        const uint32_t origin = sDesc[s].origin;
+        const int mol = (int)sDesc[s].mol;
+        const int x0 = (int)(origin & 1023u), y0 = (int)((origin >> 10) & 1023u), z0 = (int)(origin >> 20);
+        const int z1 = min(D, z0 + P.tz);
         if (total != 0u && total <= SC) {
-            unsigned t = tile;
-            const int zc = (int)(t % (unsigned)P.nzc); t /= (unsigned)P.nzc;
-            const int col = (int)(t % (unsigned)P.ncol);
-            const int mol = (int)(t / (unsigned)P.ncol);
-            const int x0 = (col / P.ncx) * kTile, y0 = (col % P.ncx) * kTile, z0 = zc * P.tz;
-            const int z1 = min(D, z0 + P.tz);
             char* const out_mol = reinterpret_cast<char*>(P.out) + (size_t)mol * P.Cout * plane * es;
             const int ncells = kCellsXY * ((z1 - z0 + CZ - 1) / CZ);
             mbar_wait(&full[s], (it / ND) & 1u);
@@ -1260,14 +1259,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
                 if (tid == 0) produce(false);   // keep the ring topped up without ever blocking
             }
         } else if (total == 0u) {
-            unsigned t = tile;
-            const int zc = (int)(t % (unsigned)P.nzc); t /= (unsigned)P.nzc;
-            const int col = (int)(t % (unsigned)P.ncol);
-            const int mol = (int)(t / (unsigned)P.ncol);
-            const int z0 = zc * P.tz;
             zero_fill_tile<O16, kPipeThreads>(reinterpret_cast<char*>(P.out) + (size_t)mol * P.Cout * plane * es, plane, D,
-                                              (col / P.ncx) * kTile, (col % P.ncx) * kTile, z0, min(D, z0 + P.tz),
-                                              P.c_begin, P.c_end, tid);
+                                              x0, y0, z0, z1, P.c_begin, P.c_end, tid);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
