@@ -128,6 +128,18 @@ int mvx_voxelize(const mvx_grid_spec *spec, const mvx_batch *batch, void *out, v
                  size_t workspace_bytes, void *stream);
 
 /*
+ * mvx_voxelize with the work split over two streams, for a caller that voxelizes a sequence of batches: the per-atom prep and
+ * the binning kernels (4 % of a ligand step) go to `bin_stream`, `bin_done_event` (a cudaEvent_t of the caller) is recorded
+ * there, and the voxelize kernel goes to `vox_stream` behind that event.  On `bin_stream` the work is sized to fit on the SMs
+ * NEXT TO the HBM-bound voxelize kernel of the previous batch still running on `vox_stream` (128-thread CTAs; the ligand
+ * voxelize kernel runs register-capped), so batch k+1's binning hides behind batch k's output writes.  The caller owns the
+ * ordering: `bin_stream` must wait (cudaStreamWaitEvent) until this batch's inputs are complete and until the voxelize kernel
+ * that last used `workspace` has finished — i.e. use two workspaces alternately.  Results are those of mvx_voxelize, bit for bit.
+ */
+int mvx_voxelize_split(const mvx_grid_spec *spec, const mvx_batch *batch, void *out, void *workspace,
+                       size_t workspace_bytes, void *bin_stream, void *vox_stream, void *bin_done_event);
+
+/*
  * Same, with HOST input buffers (what a numpy caller of the reference holds): copies the inputs
  * to the device, voxelizes into the DEVICE buffer `out`, and copies the device status word back
  * (one synchronisation).  `workspace` must hold mvx_workspace_bytes() + mvx_host_staging_bytes().

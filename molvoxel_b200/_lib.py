@@ -145,6 +145,8 @@ def lib():
         L.mvx_host_staging_bytes.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch), ctypes.POINTER(sz)]
         L.mvx_voxelize.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch), vp, vp, sz, vp]
         L.mvx_voxelize_host.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch), vp, vp, sz, vp]
+        L.mvx_voxelize_split.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch), vp, vp, sz, vp, vp, vp]
+        L.mvx_voxelize_split.restype = ctypes.c_int
         L.mvx_check_status.argtypes = [vp, vp]
         L.mvx_launches_per_call.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch)]
         L.mvx_voxelize_form.argtypes = [ctypes.POINTER(GridSpec), ctypes.POINTER(Batch)]
@@ -169,7 +171,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "mvx_version", "mvx_last_error", "mvx_workspace_bytes", "mvx_host_staging_bytes", "mvx_voxelize",
     "mvx_voxelize_host", "mvx_check_status", "mvx_launches_per_call", "mvx_voxelize_form", "mvx_profile_begin",
-    "mvx_profile_end", "mvx_random_transforms", "mvx_synth_ligands", "mvx_compact_bricks",
+    "mvx_profile_end", "mvx_random_transforms", "mvx_synth_ligands", "mvx_compact_bricks", "mvx_voxelize_split",
 ]
 
 

@@ -35,12 +35,12 @@ constexpr size_t kAlign = 256;
 struct Profile {
     bool active = false;
     int max_calls = 0, calls = 0;
-    cudaEvent_t* ev = nullptr;   // 4 events per call: before prep, after prep, after bin, after voxelize
+    cudaEvent_t* ev = nullptr;   // 5 events per call: before prep, after prep, after bin (binning stream); before / after voxelize
 };
 thread_local Profile g_prof;
 
 void prof_mark(cudaStream_t st, int slot) {
-    if (g_prof.active && g_prof.calls < g_prof.max_calls) cudaEventRecord(g_prof.ev[g_prof.calls * 4 + slot], st);
+    if (g_prof.active && g_prof.calls < g_prof.max_calls) cudaEventRecord(g_prof.ev[g_prof.calls * 5 + slot], st);
 }
 size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
@@ -328,8 +328,17 @@ int mvx_voxelize_form(const mvx_grid_spec* spec, const mvx_batch* batch) {
     return rc != MVX_OK ? rc : pl.form;
 }
 
-int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, void* workspace,
-                 size_t workspace_bytes, void* stream) {
+}  // extern "C"
+
+namespace {
+// One call's launches.  st: the stream of the per-atom prep and the binning kernels; st_vox: the stream of the voxelize
+// kernel(s).  When they differ (mvx_voxelize_split) `bin_done` orders the voxelize kernel after the binning, prep / binning
+// use 128-thread CTAs and the cells form its register-capped instance, so that both fit on an SM next to the voxelize
+// CTAs of the PREVIOUS call that are still running on st_vox.
+int enqueue(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, void* workspace, size_t workspace_bytes,
+            cudaStream_t st, cudaStream_t st_vox, cudaEvent_t bin_done) {
+    const bool split = st != st_vox;
+    const int pt = split ? 128 : 256;   // threads per CTA of prep / bin
     Plan pl;
     int rc = make_plan(spec, batch, &pl);
     if (rc != MVX_OK) return rc;
@@ -338,7 +347,6 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
     if (!workspace || workspace_bytes < pl.total) return fail(MVX_ERR_WORKSPACE, "workspace too small");
     if ((uintptr_t)workspace % kAlign != 0) return fail(MVX_ERR_WORKSPACE, "workspace must be 256-byte aligned");
     if ((uintptr_t)out % 16 != 0) return fail(MVX_ERR_BAD_SHAPE, "out must be 16-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
     int* status = (int*)(ws + pl.off_status);
     mvx::AtomRec* recs = (mvx::AtomRec*)(ws + pl.off_recs);
@@ -381,8 +389,8 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         pp.alayers = layered(pl.form) ? (uint32_t*)(ws + pl.off_alayers) : nullptr;
         pp.kcnt = layered(pl.form) ? (uint32_t*)(ws + pl.off_kcnt) : nullptr;
         pp.nzc = pl.nzc; pp.tz = pl.tz; pp.ncol = pl.ncol; pp.nl = pl.nlayers; pp.zl = pl.zl; pp.tau_lin = pl.tau_lin; pp.tau_quad = pl.tau_quad;
-        const unsigned grid = (unsigned)((N + 255) / 256);
-        mvx::mvx_prep_kernel<<<grid, 256, 0, st>>>(pp);
+        const unsigned grid = (unsigned)((N + pt - 1) / pt);
+        mvx::mvx_prep_kernel<<<grid, pt, 0, st>>>(pp);
         MVX_CUDA_OK(cudaGetLastError());
     }
     prof_mark(st, 1);
@@ -431,9 +439,9 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         ep.types = batch->types; ep.entries = entries;
         const bool expand = pl.form == FORM_CELLS && N > 0;
         if (groups <= 1 && expand) {   // many small molecules: bin and expand in one launch
-            mvx::mvx_bin_expand_kernel<<<(unsigned)B, 256, smem, st>>>(bp, ep);
+            mvx::mvx_bin_expand_kernel<<<(unsigned)B, pt, smem, st>>>(bp, ep);
         } else if (groups <= 1) {
-            mvx::mvx_bin_kernel<<<(unsigned)B, 256, smem, st>>>(bp);
+            mvx::mvx_bin_kernel<<<(unsigned)B, pt, smem, st>>>(bp);
         } else {   // few large molecules: spread each molecule's columns over several CTAs
             mvx::mvx_bin_count_kernel<<<(unsigned)(B * groups), 256, 0, st>>>(bp, groups);
             MVX_CUDA_OK(cudaGetLastError());
@@ -447,8 +455,15 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
         }
     }
     prof_mark(st, 2);
+    if (split) {
+        MVX_CUDA_OK(cudaEventRecord(bin_done, st));
+        MVX_CUDA_OK(cudaStreamWaitEvent(st_vox, bin_done, 0));
+        st = st_vox;
+    }
+    prof_mark(st, 3);
     {
         mvx::VoxParams vp;
+        vp.lean = split ? 1 : 0;
         vp.res = pl.geo.res; vp.half_width = pl.geo.half_width; vp.sigma = spec->sigma;
         vp.tau_lin = pl.tau_lin; vp.tau_quad = pl.tau_quad;
         vp.dim = spec->dimension; vp.ncx = pl.geo.ncx; vp.ncol = pl.ncol; vp.nzc = pl.nzc; vp.tz = pl.tz;
@@ -489,9 +504,24 @@ int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, v
                                    (unsigned)nblk, st));
         }
     }
-    prof_mark(st, 3);
+    prof_mark(st, 4);
     if (g_prof.active && g_prof.calls < g_prof.max_calls) ++g_prof.calls;
     return MVX_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int mvx_voxelize(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+    return enqueue(spec, batch, out, workspace, workspace_bytes, (cudaStream_t)stream, (cudaStream_t)stream, nullptr);
+}
+
+int mvx_voxelize_split(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, void* workspace,
+                       size_t workspace_bytes, void* bin_stream, void* vox_stream, void* bin_done_event) {
+    if (bin_stream == vox_stream) return enqueue(spec, batch, out, workspace, workspace_bytes, (cudaStream_t)vox_stream, (cudaStream_t)vox_stream, nullptr);
+    if (!bin_done_event) return fail(MVX_ERR_NULL_POINTER, "bin_done_event is NULL");
+    return enqueue(spec, batch, out, workspace, workspace_bytes, (cudaStream_t)bin_stream, (cudaStream_t)vox_stream, (cudaEvent_t)bin_done_event);
 }
 
 int mvx_random_transforms(uint64_t rng_seed, uint64_t rng_offset, int32_t num_mols, int32_t transform_flags,
@@ -552,8 +582,8 @@ int mvx_compact_bricks(const mvx_grid_spec* spec, const mvx_batch* batch, const 
 int mvx_profile_begin(int max_calls) {
     if (g_prof.active) return fail(MVX_ERR_UNSUPPORTED, "a profile is already open on this thread");
     if (max_calls < 1) return fail(MVX_ERR_BAD_SHAPE, "max_calls must be >= 1");
-    g_prof.ev = new cudaEvent_t[(size_t)max_calls * 4];
-    for (int i = 0; i < max_calls * 4; ++i) MVX_CUDA_OK(cudaEventCreate(&g_prof.ev[i]));
+    g_prof.ev = new cudaEvent_t[(size_t)max_calls * 5];
+    for (int i = 0; i < max_calls * 5; ++i) MVX_CUDA_OK(cudaEventCreate(&g_prof.ev[i]));
     g_prof.max_calls = max_calls; g_prof.calls = 0; g_prof.active = true;
     return MVX_OK;
 }
@@ -563,15 +593,16 @@ int mvx_profile_end(double* ms_prep, double* ms_bin, double* ms_voxelize, int* n
     double t[3] = {0, 0, 0};
     int rc = MVX_OK;
     if (g_prof.calls > 0) {
-        if (cudaEventSynchronize(g_prof.ev[(g_prof.calls - 1) * 4 + 3]) != cudaSuccess) rc = MVX_ERR_CUDA;
+        if (cudaEventSynchronize(g_prof.ev[(g_prof.calls - 1) * 5 + 4]) != cudaSuccess) rc = MVX_ERR_CUDA;
+        static const int first[3] = {0, 1, 3};   // prep = e0..e1, bin = e1..e2, voxelize = e3..e4
         for (int c = 0; c < g_prof.calls && rc == MVX_OK; ++c)
             for (int k = 0; k < 3; ++k) {
                 float ms = 0.f;
-                if (cudaEventElapsedTime(&ms, g_prof.ev[c * 4 + k], g_prof.ev[c * 4 + k + 1]) != cudaSuccess) rc = MVX_ERR_CUDA;
+                if (cudaEventElapsedTime(&ms, g_prof.ev[c * 5 + first[k]], g_prof.ev[c * 5 + first[k] + 1]) != cudaSuccess) rc = MVX_ERR_CUDA;
                 t[k] += ms;
             }
     }
-    for (int i = 0; i < g_prof.max_calls * 4; ++i) cudaEventDestroy(g_prof.ev[i]);
+    for (int i = 0; i < g_prof.max_calls * 5; ++i) cudaEventDestroy(g_prof.ev[i]);
     delete[] g_prof.ev;
     if (ms_prep) *ms_prep = t[0];
     if (ms_bin) *ms_bin = t[1];

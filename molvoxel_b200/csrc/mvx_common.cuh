@@ -150,6 +150,7 @@ struct VoxParams {
     const TileDesc* tdesc;     // pipelined form; for the tile form: non-null = only tiles with more than pipe_sc entries
     int pipe_sc;               // pipelined form: largest tile (entries) it takes; larger ones go to the tile form
     int pipe_q;                // pipelined form: float4 words of the shared-memory entry ring
+    int lean;                  // cells form: the register-capped instance (the next batch's binning shares the SMs)
     void* out;                 // (B, Cout, D, D, D), element type by out_kind
     int out_kind;              // 0 fp32 (reference), 1 bf16, 2 fp16 (reduced-precision output)
 };

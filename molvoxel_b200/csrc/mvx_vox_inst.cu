@@ -56,6 +56,14 @@ cudaError_t launch_form_out(const VoxParams& vp, int form, int nv, unsigned grid
     } else if (form == FORM_CELLS) {
         constexpr size_t smem = cells_smem_bytes<MODE, CH>();
         static DeviceSet cfg;
+        if constexpr (MODE == 1 && CH >= 12) {
+            if (vp.lean) {
+                static DeviceSet cfg_l;
+                { cudaError_t e = set_smem(mvx_voxelize_cells_lean_kernel<MODE, CH, BINARY, O16>, smem, &cfg_l); if (e != cudaSuccess) return e; }
+                mvx_voxelize_cells_lean_kernel<MODE, CH, BINARY, O16><<<grid, kThreads, smem, st>>>(vp);
+                return cudaGetLastError();
+            }
+        }
         { cudaError_t e = set_smem(mvx_voxelize_cells_kernel<MODE, CH, BINARY, O16>, smem, &cfg); if (e != cudaSuccess) return e; }
         mvx_voxelize_cells_kernel<MODE, CH, BINARY, O16><<<grid, kThreads, smem, st>>>(vp);
     } else if (nv == 4) {

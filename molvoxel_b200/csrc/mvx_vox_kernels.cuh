@@ -276,7 +276,7 @@ constexpr size_t cells_smem_bytes() {
 }
 
 template <int MODE, int CH, bool BINARY, bool O16>
-__global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cells_kernel(const VoxParams P) {
+__device__ __forceinline__ void cells_body(const VoxParams& P) {
     constexpr int NT = kThreads, LPR = 4;   // 4 lanes (one float4 each) along z per row: cells of 2 x 4 x 16 voxels
     constexpr int NW = NT / 32;             // warps per CTA
     constexpr int SC = 2 * NT;    // atoms staged per round
@@ -540,6 +540,19 @@ __global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cell
     }
 }
 
+
+template <int MODE, int CH, bool BINARY, bool O16>
+__global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cells_kernel(const VoxParams P) {
+    cells_body<MODE, CH, BINARY, O16>(P);
+}
+
+// The same kernel capped at 112 registers: two CTAs leave 8 192 registers of an SM free, room for one 128-thread CTA of
+// the per-atom prep / binning kernels of the NEXT batch (mvx_voxelize_split: they run on a second stream in the shadow of
+// this HBM-bound kernel).  Costs a 24-byte spill, which a write-bound kernel does not notice.
+template <int MODE, int CH, bool BINARY, bool O16>
+__global__ void __maxnreg__(112) mvx_voxelize_cells_lean_kernel(const VoxParams P) {
+    cells_body<MODE, CH, BINARY, O16>(P);
+}
 
 // ---------------------------------------------------------------------------------------------
 // voxelize, "tile" form (the main path; needs D % 4 == 0).  One CTA per tile of 8 x 8 x tz voxels.

@@ -89,6 +89,11 @@ class Voxelizer:
         # the numpy / numba backends add the translation twice when a rotation is also requested
         # (numpy/transform.py:56-59); translate_once=True gives the torch backend's single addition
         self.translate_once = bool(kwargs.get("translate_once", False))
+        # overlap=True (default): host batches passed with non_blocking=True run their prep / binning on a second stream next to
+        # the previous call's voxelize kernel where that pays (ligand sweeps); device inputs opt in with inputs_ready=
+        self.overlap = bool(kwargs.get("overlap", True))
+        self._overlap = None
+        self._last_ws = None
         self._ws = None
         self._ws_need = {}
         self._pipe = None
@@ -166,6 +171,8 @@ class Voxelizer:
         if device != self.device:
             self.device = device
             self._ws = None
+            self._overlap = None
+            self._pipe = None
         if blockdim is not None:
             self.blockdim = int(blockdim)
         return self
@@ -252,15 +259,19 @@ class Voxelizer:
     # ---- batched driver (new, additive; per-molecule semantics = B independent reference calls) ----
     def forward_types_batch(self, coords, mol_offsets, centers, types, radii, num_channels,
                             random_translation: float = 0.0, random_rotation: bool = False, out=None,
-                            non_blocking: bool = False, max_radius=None, transforms=None, rng_offset=None):
+                            non_blocking: bool = False, max_radius=None, transforms=None, rng_offset=None,
+                            inputs_ready=None):
         """CSR batch -> (B, C, D, H, W).  non_blocking=True with HOST inputs pipelines the H2D copies of this
         call behind the kernels of the previous one (pinned inputs; call check_status() to synchronise).
         max_radius: a host-known bound of an array `radii` (saves a device->host read on the device path).
         transforms: explicit rigid transforms ((B, 7) rows, a T, or a list of T) instead of random draws.
-        rng_offset: global index of the batch's first molecule for the device generator (sharded / chunked sweeps)."""
+        rng_offset: global index of the batch's first molecule for the device generator (sharded / chunked sweeps).
+        inputs_ready: DEVICE inputs only — True, or the torch.cuda.Event that completes them: the inputs do not depend on
+        work pending on the current stream, so this call's prep / binning may overlap the previous call's voxelize kernel."""
         return self._forward_batch("types", coords, mol_offsets, centers, types, radii, int(num_channels),
                                    random_translation, random_rotation, out, non_blocking=non_blocking,
-                                   max_radius=max_radius, transforms=transforms, rng_offset=rng_offset)
+                                   max_radius=max_radius, transforms=transforms, rng_offset=rng_offset,
+                                   inputs_ready=inputs_ready)
 
     def forward_features_batch(self, coords, mol_offsets, centers, features, radii,
                                random_translation: float = 0.0, random_rotation: bool = False, out=None,
@@ -368,7 +379,7 @@ class Voxelizer:
 
     def _forward_batch(self, mode, coords, mol_offsets, centers, channels, radii, C, random_translation,
                        random_rotation, out, infer_types_channels=False, max_radius=None, non_blocking=False,
-                       transforms=None, rng_offset=None):
+                       transforms=None, rng_offset=None, inputs_ready=None):
         have_cuda = self.device.type == "cuda" and torch.cuda.is_available()
         coords, centers, channels, radii = _norm(coords), _norm(centers), _norm(channels), _norm(radii)
         on_device = isinstance(coords, torch.Tensor) and coords.is_cuda
@@ -381,13 +392,17 @@ class Voxelizer:
             (coords_d, offs_d, centers_d, chan_d, radii_d), slot = self._upload_pipelined([
                 ("coords", coords), ("offs", np.asarray(mol_offsets, dtype=np.int32) if not isinstance(mol_offsets, torch.Tensor) else mol_offsets),
                 ("centers", centers), ("chan", channels), ("radii", None if _is_scalar(radii) else radii)])
+            # the copy's own event says when the inputs are complete: prep / binning of this call may then run on the
+            # binning stream next to the previous call's voxelize kernel (mvx_voxelize_split) where that applies
             res = self._forward_batch(mode, coords_d, offs_d, centers_d, chan_d, radii if _is_scalar(radii) else radii_d, C,
                                       random_translation, random_rotation, out, False, max_radius,
-                                      transforms=transforms, rng_offset=rng_offset)
+                                      transforms=transforms, rng_offset=rng_offset,
+                                      inputs_ready=slot["copied"] if self.overlap else None)
             cur = torch.cuda.current_stream(self.device)
-            ws_ptr_off = (-self._ws.data_ptr()) % 256
+            wst = self._last_ws
+            ws_ptr_off = (-wst.data_ptr()) % 256
             self._pipe["status"][slot["index"]:slot["index"] + 1].copy_(
-                self._ws[ws_ptr_off:ws_ptr_off + 4].view(torch.int32), non_blocking=True)
+                wst[ws_ptr_off:ws_ptr_off + 4].view(torch.int32), non_blocking=True)
             slot["done"].record(cur)
             return res
         D = self._dimension
@@ -465,10 +480,14 @@ class Voxelizer:
 
         keep = []   # keeps converted arrays alive until the call returns
 
+        converted = [False]   # an input had to be cast / moved / compacted: it is produced on the current stream
+
         def dev(t, dt):
-            t = t.to(self.device, dt).contiguous()
-            keep.append(t)
-            return t
+            t2 = t.to(self.device, dt).contiguous()
+            if t2 is not t and t2.data_ptr() != t.data_ptr():
+                converted[0] = True
+            keep.append(t2)
+            return t2
 
         def host(a, dt=None):
             a = np.ascontiguousarray(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a), dtype=dt)
@@ -569,19 +588,53 @@ class Voxelizer:
             if len(self._ws_need) > 256:
                 self._ws_need.clear()
             self._ws_need[key] = total
-        ws = self._workspace(total)
+        # Two-stream form (mvx_voxelize_split): the caller vouches that the device inputs are complete (`inputs_ready` =
+        # True or the event that completes them), nothing had to be converted on the current stream, and the kernel is
+        # the HBM-bound ligand form with a register-capped instance (types, 9..16 channels): prep + binning then run on
+        # a second stream in the shadow of the previous call's voxelize kernel, on alternating workspaces.
+        split = (on_device and inputs_ready is not None and inputs_ready is not False and not converted[0] and tf_rows is None
+                 and mode == "types" and 9 <= out_channels <= 16 and self.out_dtype != torch.float64
+                 and L.mvx_voxelize_form(ctypes.byref(spec), ctypes.byref(b)) == 1)
+        cur = torch.cuda.current_stream(self.device)
+        if split:
+            ov = self._overlap
+            if ov is None:
+                ov = self._overlap = {"bin": torch.cuda.Stream(self.device, priority=-1), "idx": 0,
+                                      "slots": [{"ws": None, "bin_done": torch.cuda.Event(), "free": torch.cuda.Event()} for _ in range(2)]}
+                for sl in ov["slots"]:
+                    sl["bin_done"].record(cur)   # creates the underlying cudaEvent_t
+            sl = ov["slots"][ov["idx"]]
+            ov["idx"] ^= 1
+            if sl["ws"] is None or sl["ws"].numel() < total + 256:
+                sl["ws"] = torch.empty(int(total * 1.25) + 4096, dtype=torch.uint8, device=self.device)
+            ws = sl["ws"]
+        else:
+            ws = self._workspace(total)
+        self._last_ws = ws
         ws_ptr = (ws.data_ptr() + 255) // 256 * 256
         ws_bytes = ws.numel() - (ws_ptr - ws.data_ptr())
-        fn = L.mvx_voxelize if on_device else L.mvx_voxelize_host
+
+        def launch():
+            args = (ctypes.byref(spec), ctypes.byref(b), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws_ptr), ctypes.c_size_t(ws_bytes))
+            if split:
+                bs = ov["bin"]
+                if isinstance(inputs_ready, torch.cuda.Event):
+                    bs.wait_event(inputs_ready)
+                bs.wait_event(sl["free"])        # the voxelize kernel that last read this workspace has finished
+                rc = L.mvx_voxelize_split(*args, ctypes.c_void_p(bs.cuda_stream), ctypes.c_void_p(cur.cuda_stream),
+                                          ctypes.c_void_p(sl["bin_done"].cuda_event))
+                sl["free"].record(cur)
+                for t in keep:
+                    if isinstance(t, torch.Tensor):
+                        t.record_stream(bs)
+                return rc
+            fn = L.mvx_voxelize if on_device else L.mvx_voxelize_host
+            return fn(*args, ctypes.c_void_p(cur.cuda_stream))
         if torch.cuda.current_device() == self.device.index:
-            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-            rc = fn(ctypes.byref(spec), ctypes.byref(b), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws_ptr),
-                    ctypes.c_size_t(ws_bytes), stream)
+            rc = launch()
         else:
             with torch.cuda.device(self.device):
-                stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-                rc = fn(ctypes.byref(spec), ctypes.byref(b), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws_ptr),
-                        ctypes.c_size_t(ws_bytes), stream)
+                rc = launch()
         _lib.raise_for_status(rc)
         # shapes / flags of this call (pointers are not dereferenced again): compact() finds the column occupancy the
         # binning pass left in the workspace
@@ -635,13 +688,21 @@ class Voxelizer:
             cap = n
 
     def check_status(self):
-        """Synchronise and raise if the last device-path call flagged bad types / radii (device-side validation)."""
-        if self._ws is None:
+        """Synchronise and raise if a device-path call since the last check flagged bad types / radii (device-side validation)."""
+        spaces = [w for w in [self._ws] + ([sl["ws"] for sl in self._overlap["slots"]] if self._overlap else []) if w is not None]
+        if not spaces:
             return
-        ws_ptr = (self._ws.data_ptr() + 255) // 256 * 256
+        err = None
         with torch.cuda.device(self.device):
             stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-            _lib.raise_for_status(_lib.lib().mvx_check_status(ctypes.c_void_p(ws_ptr), stream))
+            for w in spaces:
+                ws_ptr = (w.data_ptr() + 255) // 256 * 256
+                try:
+                    _lib.raise_for_status(_lib.lib().mvx_check_status(ctypes.c_void_p(ws_ptr), stream))
+                except ValueError as e:
+                    err = e
+        if err is not None:
+            raise err
         if self._pipe is not None:   # status words copied back by the pipelined (non_blocking) calls: sticky
             flags = self._sticky_flags | int(self._pipe["status"][0]) | int(self._pipe["status"][1])
             self._pipe["status"].zero_()

@@ -1071,3 +1071,36 @@ def test_compact_collation_gives_identical_grids():
     assert torch.equal(a, b)
     nbytes = lambda d: sum(v.nbytes for v in d.values() if isinstance(v, np.ndarray))   # noqa: E731
     assert nbytes(small) < 0.4 * nbytes(plain)
+
+
+def test_two_stream_form_equals_the_single_stream_form_bitwise():
+    """mvx_voxelize_split (prep / binning of call k+1 on a second stream next to the voxelize kernel of call k, two
+    workspaces, register-capped ligand kernel) over a sequence of distinct batches: identical grids, device inputs with
+    inputs_ready=True and pinned host inputs with non_blocking=True; status flags still arrive."""
+    rng = np.random.default_rng(44)
+    C, B = 9, 96
+    batches = [ligand_batch(rng, B, C) for _ in range(5)]
+    plain = mv.create_voxelizer(0.5, 64, "scalar", "gaussian", library="b200", overlap=False)
+    fast = mv.create_voxelizer(0.5, 64, "scalar", "gaussian", library="b200")
+    want = [plain.forward_types_batch(c, o, None, t, 1.0, C).clone() for o, c, t in batches]
+    dev = [(torch.from_numpy(c).cuda(), torch.from_numpy(o).cuda(), torch.from_numpy(t).cuda()) for o, c, t in batches]
+    torch.cuda.synchronize()
+    ring = [torch.empty_like(want[0]) for _ in range(2)]
+    got = []
+    for k, (c, o, t) in enumerate(dev):
+        got.append(fast.forward_types_batch(c, o, None, t, 1.0, C, out=ring[k & 1], inputs_ready=True).clone())
+    fast.check_status()
+    assert fast._overlap is not None, "the two-stream form was not taken"
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    pinned = [tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy() for a in (c, o, t)) for o, c, t in batches]
+    got = [fast.forward_types_batch(c, o, None, t, 1.0, C, out=ring[k & 1], non_blocking=True,
+                                    random_translation=0.5, random_rotation=True, rng_offset=7 * k).clone() for k, (c, o, t) in enumerate(pinned)]
+    fast.check_status()
+    for k, ((o, c, t), g) in enumerate(zip(batches, got)):
+        assert torch.equal(g, plain.forward_types_batch(c, o, None, t, 1.0, C, random_translation=0.5, random_rotation=True, rng_offset=7 * k))
+    bad = batches[0][2].copy()
+    bad[5] = 11
+    fast.forward_types_batch(dev[0][0], dev[0][1], None, torch.from_numpy(bad).cuda(), 1.0, C, inputs_ready=True)
+    with pytest.raises(ValueError):
+        fast.check_status()
