@@ -115,6 +115,8 @@ def workload_config(args, world: int) -> dict:
     cfg = {"workload": f"{args.workload}: {w['desc']}", "channels": w["C"], "grid": f"{w['dim']}^3", "resolution": w["res"],
            "density": w["density"], "radii_type": w["radii_type"], "chunk": args.batch or w["batch"],
            "augment": bool(args.augment), "compat_blockdim": 8, "out_dtype": args.out_dtype}
+    if getattr(args, "channels_last", False):
+        cfg["out_layout"] = "channels-last (B, D, H, W, C) — not the headline (reference) layout"
     if is_sweep(args.workload):
         cfg["molecules"] = args.molecules or w["molecules"]
         cfg["inputs"] = "distinct molecules from a counter-based generator keyed by the global molecule index (mvx_synth_ligands)"
@@ -447,10 +449,10 @@ def run_b200_arm(args):
     out_dt = getattr(torch, args.out_dtype)
     esize = 4 if args.out_dtype == "float32" else 2
     vox = mv.create_voxelizer(w["res"], D, w["radii_type"], w["density"], library="b200", device=dev, out_dtype=out_dt,
-                              seed=SWEEP_SEED, overlap=not args.no_overlap)
+                              seed=SWEEP_SEED, overlap=not args.no_overlap, channels_last=args.channels_last)
     ch = Chunks(name, args, rank, world, dev)
     B = ch.B
-    ring = [torch.empty((B, C, D, D, D), dtype=out_dt, device=dev) for _ in range(2)]
+    ring = [vox.get_empty_grid(C, B) for _ in range(2)]   # (B, C, D, D, D); physically (B, D, D, D, C) with --channels-last
     rt, rr = (0.5, True) if args.augment else (0.0, False)
     fwd = {"types": lambda a, **kw: vox.forward_types_batch(a["coords"], a["offs"], a["centers"], a["chan"], a["radii"], C, rt, rr, **kw),
            "features": lambda a, **kw: vox.forward_features_batch(a["coords"], a["offs"], a["centers"], a["chan"], a["radii"], rt, rr, **kw)}[w["mode"]]
@@ -548,8 +550,9 @@ def run_b200_arm(args):
     extras = {}
     if not ch.sweep:
         extras["plain_inputs"] = plain_inputs_leg(ch, vox, fwd, ring, timed, steps, warm_steps, world, K, n_calls)
-    extras["with_grid_d2h"] = grid_d2h_leg(ch, vox, fwd, ring, esize, C, D, out_dt, world, dev)
-    if esize == 4:
+    if not args.channels_last:
+        extras["with_grid_d2h"] = grid_d2h_leg(ch, vox, fwd, ring, esize, C, D, out_dt, world, dev)
+    if esize == 4 and not args.channels_last:
         extras["with_grid_d2h_sparse"] = grid_d2h_sparse_leg(ch, vox, fwd, ring, C, D, world, dev)
     if args.gather and world > 1:
         extras["gather"] = gather_leg(ring[0], world, dev)
@@ -946,6 +949,7 @@ def main():
     ap.add_argument("--augment", action="store_true", help="random_translation=0.5, random_rotation=True (the reference's batched use-case), drawn on the device")
     ap.add_argument("--gather", action="store_true", help="N > 1: also time the optional NCCL all-gather of finished grids")
     ap.add_argument("--no-overlap", action="store_true", help="keep every call's prep / binning on the caller's stream (A/B of mvx_voxelize_split)")
+    ap.add_argument("--channels-last", action="store_true", help="grids in the channels-last layout (B, D, H, W, C) (SURVEY row f3; not the headline layout)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--atoms", type=int, default=0, help="atoms per molecule (density sweeps; default: the workload's own)")

@@ -38,6 +38,10 @@ enum { MVX_RADII_SCALAR = 0, MVX_RADII_CHANNEL_WISE = 1, MVX_RADII_ATOM_WISE = 2
 enum { MVX_MODE_SINGLE = 0, MVX_MODE_TYPES = 1, MVX_MODE_FEATURES = 2 };            /* base/voxelizer.py:121-128 */
 enum { MVX_F32 = 0, MVX_F64 = 1, MVX_U8 = 2, MVX_F16 = 3 };   /* U8 / F16: compact feature rows only */
 enum { MVX_OUT_F32 = 0, MVX_OUT_BF16 = 1, MVX_OUT_F16 = 2, MVX_OUT_F64 = 3 };   /* element type of the output grid */
+/* Memory layout of the output grid.  CDHW is the reference's (numpy/voxelizer.py:60-70: channel, x, y, z).  DHWC is the
+ * channels-last form the reference README writes its formulas in (README.md:138-142) and 3-D CNNs in
+ * torch.channels_last_3d consume: (B, D, H, W, C), the C channels of one voxel contiguous.  Same values, bit for bit. */
+enum { MVX_LAYOUT_CDHW = 0, MVX_LAYOUT_DHWC = 1 };
 /* How the caller held the SCALAR radius.  numpy's promotion rules (NEP 50) make the reference's arithmetic depend on it:
  * a python float is weak (fp32 division dist32 / r, fp64 clip bounds); an np.float64 scalar is strong (fp64 division and
  * Gaussian, numpy/voxelizer.py:546-548); an np.float32 scalar demotes the python-float clip bounds to fp32 (:487-488). */
@@ -114,13 +118,15 @@ typedef struct mvx_batch {
     uint64_t       rng_offset;      /* ... and global index of this batch's first molecule */
     double         random_translation;   /* device-drawn transforms: translation ~ U(-t, t)^3, rounded to fp32
                                             (numpy/transform.py:74-76) */
+    int32_t        out_layout;      /* MVX_LAYOUT_CDHW (default, the reference's) | MVX_LAYOUT_DHWC (channels-last) */
 } mvx_batch;
 
 /* Bytes of device workspace mvx_voxelize needs for this spec/batch (256-byte aligned base). */
 int mvx_workspace_bytes(const mvx_grid_spec *spec, const mvx_batch *batch, size_t *out_bytes);
 
 /*
- * Voxelize a batch: out is a DEVICE buffer (B, out_channels, D, H, W) of batch->out_dtype (float32 by default), contiguous,
+ * Voxelize a batch: out is a DEVICE buffer (B, out_channels, D, H, W) — or (B, D, H, W, out_channels) with
+ * batch->out_layout = MVX_LAYOUT_DHWC — of batch->out_dtype (float32 by default), contiguous,
  * written exactly once per voxel (zeros included).  Work is enqueued on `stream`
  * (a cudaStream_t; NULL = legacy default stream); no host synchronisation happens inside.
  */

@@ -37,6 +37,7 @@ MODE = {"single": 0, "types": 1, "features": 2}
 FORM_KERNEL = {0: "mvx_voxelize_kernel", 1: "mvx_voxelize_cells_kernel", 3: "mvx_voxelize_tiles_kernel", 4: "mvx_voxelize_pipe_kernel"}
 OUT_DTYPE = {"float32": 0, "bfloat16": 1, "float16": 2, "float64": 3}
 RADIUS_PYFLOAT, RADIUS_NP_F64, RADIUS_NP_F32 = 0, 1, 2
+LAYOUT_CDHW, LAYOUT_DHWC = 0, 1
 TF_ROTATE, TF_TRANSLATE, TF_TRANSLATE_ONCE = 1, 2, 4
 
 
@@ -76,6 +77,7 @@ class Batch(ctypes.Structure):
         ("rng_seed", ctypes.c_uint64),
         ("rng_offset", ctypes.c_uint64),
         ("random_translation", ctypes.c_double),
+        ("out_layout", ctypes.c_int32),
     ]
 
 

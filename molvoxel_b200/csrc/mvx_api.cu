@@ -80,6 +80,7 @@ int check_args(const mvx_grid_spec* s, const mvx_batch* b) {
     if (b->mode != MVX_MODE_TYPES && b->out_channels != C) return fail(MVX_ERR_BAD_SHAPE, "Output grid dimension incorrect");
     if (b->out_dtype < MVX_OUT_F32 || b->out_dtype > MVX_OUT_F64) return fail(MVX_ERR_BAD_ENUM, "out_dtype");
     if (b->features_dtype != MVX_F32 && b->features_dtype != MVX_U8 && b->features_dtype != MVX_F16) return fail(MVX_ERR_BAD_ENUM, "features_dtype");
+    if (b->out_layout != MVX_LAYOUT_CDHW && b->out_layout != MVX_LAYOUT_DHWC) return fail(MVX_ERR_BAD_ENUM, "out_layout");
     if (b->radius_kind < MVX_RADIUS_PYFLOAT || b->radius_kind > MVX_RADIUS_NP_F32) return fail(MVX_ERR_BAD_ENUM, "radius_kind");
     if (b->transform_flags & ~(MVX_TF_ROTATE | MVX_TF_TRANSLATE | MVX_TF_TRANSLATE_ONCE)) return fail(MVX_ERR_BAD_ENUM, "transform_flags");
     if ((b->transform_flags & MVX_TF_TRANSLATE) && !b->transforms && !(b->random_translation > 0.0))
@@ -470,6 +471,7 @@ int enqueue(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, void* 
         vp.C = C; vp.Cout = batch->out_channels; vp.maxcols = pl.maxcols; vp.cull = pl.geo.nb > 1;
         vp.mol_offsets = batch->mol_offsets; vp.recs = recs; vp.bins = bins; vp.lists = lists;
         vp.types = batch->types; vp.features = (const float*)batch->features; vp.chan_radii = nullptr; vp.out = out; vp.out_kind = batch->out_dtype;
+        vp.clast = batch->out_layout == MVX_LAYOUT_DHWC;
         vp.entries = entries; vp.masks = legacy_masks;
         vp.nlayers = pl.nlayers; vp.zl = pl.zl; vp.es4 = pl.es4;
         vp.lent = (const float4*)(ws + pl.off_lent);
@@ -486,6 +488,7 @@ int enqueue(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, void* 
             fp.dim = spec->dimension; fp.ncx = pl.geo.ncx; fp.ncol = pl.ncol; fp.mode = batch->mode; fp.C = C;
             fp.Cout = batch->out_channels; fp.maxcols = pl.maxcols; fp.binary = binary;
             fp.scalar_radius = spec->radii_type == MVX_RADII_SCALAR;
+            fp.clast = batch->out_layout == MVX_LAYOUT_DHWC;
             fp.mol_offsets = batch->mol_offsets; fp.recs = recs; fp.bins = bins; fp.lists = lists;
             fp.types = batch->types; fp.features = (const float*)batch->features; fp.chan_radii = chan_feat ? batch->radii : nullptr;
             fp.out = (double*)out;
@@ -560,6 +563,7 @@ int mvx_compact_bricks(const mvx_grid_spec* spec, const mvx_batch* batch, const 
     int rc = make_plan(spec, batch, &pl);
     if (rc != MVX_OK) return rc;
     if (batch->out_dtype != MVX_OUT_F32) return fail(MVX_ERR_UNSUPPORTED, "brick compaction needs float32 grids");
+    if (batch->out_layout != MVX_LAYOUT_CDHW) return fail(MVX_ERR_UNSUPPORTED, "brick compaction needs the (B, C, D, H, W) layout");
     if (!count) return fail(MVX_ERR_NULL_POINTER, "count is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     MVX_CUDA_OK(cudaMemsetAsync(count, 0, sizeof(uint32_t), st));

@@ -771,6 +771,7 @@ struct VoxF64Params {
     double res, half_width, sigma, radius;
     int dim, ncx, ncol, mode, C, Cout, maxcols, binary;
     int scalar_radius;          // 1: every atom uses `radius` (python float); 0: the atom record's fp32 radius, widened
+    int clast;                  // 1: channels-last output (B, D, D, D, Cout)
     const int32_t* mol_offsets;
     const AtomRec* recs;
     const uint2* bins;
@@ -838,7 +839,7 @@ __global__ void __launch_bounds__(256) mvx_voxelize_f64_kernel(const VoxF64Param
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-                if (c0 + c < P.Cout) out_mol[(size_t)(c0 + c) * plane + vox] = acc[c];
+                if (c0 + c < P.Cout) out_mol[P.clast ? vox * (size_t)P.Cout + (size_t)(c0 + c) : (size_t)(c0 + c) * plane + vox] = acc[c];
         }
     }
 }

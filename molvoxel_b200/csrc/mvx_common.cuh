@@ -153,6 +153,7 @@ struct VoxParams {
     int lean;                  // cells form: the register-capped instance (the next batch's binning shares the SMs)
     void* out;                 // (B, Cout, D, D, D), element type by out_kind
     int out_kind;              // 0 fp32 (reference), 1 bf16, 2 fp16 (reduced-precision output)
+    int clast;                 // 1: channels-last output (B, D, D, D, Cout) — the channels of a voxel are contiguous (row f3)
 };
 
 // ---- shared-memory geometry of the voxelize forms (the host plan needs it as well) ----

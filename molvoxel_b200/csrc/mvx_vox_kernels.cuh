@@ -97,6 +97,90 @@ __device__ __forceinline__ void zero_fill_tile(char* out_mol, size_t plane, int 
     else zero_fill_items<4, 2, NT>(out_mol, plane, D, x0, y0, z0, z1, c_begin, c_end, tid);
 }
 
+// ---- channels-last output (B, D, H, W, Cout), SURVEY row f3: the Cout channels of one voxel are contiguous ----
+template <bool O16>
+__device__ __forceinline__ void store_chan1(char* p, float v, int kind) {
+    if (!O16) __stcs(reinterpret_cast<float*>(p), v);
+    else if (kind == 1) *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16_rn(v);
+    else *reinterpret_cast<__half*>(p) = __float2half_rn(v);
+}
+template <bool O16>
+__device__ __forceinline__ void store_chan4(char* p, float a, float b, float c, float d, int kind) {
+    const float v[4] = {a, b, c, d};
+    store_vox<O16>(p, v, kind);   // four consecutive channels of one voxel: one 16-byte (fp32) / 8-byte (16-bit) store
+}
+// One lane's CH channels x 4 z voxels -> out, either layout.  (x, y, z) is the lane's first voxel, c0 the chunk's first channel.
+template <int CH, bool O16>
+__device__ __forceinline__ void store_lane(const VoxParams& P, char* out_mol, size_t plane, int D, int x, int y, int z,
+                                           int c0, const float (&acc)[CH][4]) {
+    constexpr int es = O16 ? 2 : 4;
+    if (!P.clast) {
+        char* p = out_mol + ((size_t)c0 * plane + ((size_t)x * D + y) * D + z) * es;
+        const size_t pstride = plane * es;
+        if (c0 + CH <= P.c_end) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c, p += pstride) store_vox<O16>(p, acc[c], P.out_kind);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CH; ++c, p += pstride)
+                if (c0 + c < P.c_end) store_vox<O16>(p, acc[c], P.out_kind);
+        }
+        return;
+    }
+    const size_t vstride = (size_t)P.Cout * es;
+    char* p = out_mol + (((size_t)x * D + y) * D + z) * vstride + (size_t)c0 * es;
+    const bool vec = CH % 4 == 0 && (P.Cout & 3) == 0 && (c0 & 3) == 0 && c0 + CH <= P.c_end;
+#pragma unroll
+    for (int k = 0; k < 4; ++k, p += vstride) {
+        if (CH % 4 == 0 && vec) {
+#pragma unroll
+            for (int c = 0; c + 3 < CH; c += 4) store_chan4<O16>(p + c * es, acc[c][k], acc[c + 1][k], acc[c + 2][k], acc[c + 3][k], P.out_kind);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+                if (c0 + c < P.c_end) store_chan1<O16>(p + c * es, acc[c][k], P.out_kind);
+        }
+    }
+}
+// Zero fill of one tile in the channels-last layout: per (x, y) row the z range x all channels is one contiguous run.
+template <int ES, int NT>
+__device__ __forceinline__ void zero_fill_tile_clast(char* out_mol, int D, int Cout, int x0, int y0, int z0, int z1,
+                                                     int c_begin, int c_end, int tid) {
+    const int nz = z1 - z0;
+    const size_t vstride = (size_t)Cout * ES;
+    const size_t rowbytes = (size_t)nz * vstride;
+    if (c_begin == 0 && c_end == Cout && (rowbytes & 15) == 0 && (((size_t)D * vstride) & 15) == 0 && (((size_t)z0 * vstride) & 15) == 0) {
+        const int q = (int)(rowbytes >> 4);
+        const int total = kTile * kTile * q;
+        const int qstep = NT / q, rstep = NT - qstep * q;
+        int row = tid / q, w = tid - row * q;
+        for (int i = tid; i < total; i += NT) {
+            const int x = x0 + (row >> 3), y = y0 + (row & 7);
+            if (x < D && y < D)
+                __stcs(reinterpret_cast<float4*>(out_mol + (((size_t)x * D + y) * D + z0) * vstride) + w, make_float4(0.f, 0.f, 0.f, 0.f));
+            row += qstep; w += rstep;
+            if (w >= q) { w -= q; ++row; }
+        }
+    } else {
+        const int nc = c_end - c_begin, per_row = nz * nc, total = kTile * kTile * per_row;
+        for (int i = tid; i < total; i += NT) {
+            const int row = i / per_row, r = i - row * per_row, zz = r / nc, c = c_begin + (r - zz * nc);
+            const int x = x0 + (row >> 3), y = y0 + (row & 7);
+            if (x < D && y < D) {
+                char* p = out_mol + (((size_t)x * D + y) * D + z0 + zz) * vstride + (size_t)c * ES;
+                if (ES == 4) *reinterpret_cast<float*>(p) = 0.f;
+                else *reinterpret_cast<uint16_t*>(p) = (uint16_t)0;
+            }
+        }
+    }
+}
+// Zero fill of a tile, either layout.
+template <bool O16, int NT>
+__device__ __forceinline__ void zero_tile(const VoxParams& P, char* out_mol, size_t plane, int D, int x0, int y0, int z0, int z1, int tid) {
+    if (!P.clast) zero_fill_tile<O16, NT>(out_mol, plane, D, x0, y0, z0, z1, P.c_begin, P.c_end, tid);
+    else zero_fill_tile_clast<(O16 ? 2 : 4), NT>(out_mol, D, P.Cout, x0, y0, z0, z1, P.c_begin, P.c_end, tid);
+}
+
 template <int MODE, int CH, bool BINARY, int NV, bool O16>
 __global__ void __launch_bounds__(kThreads) mvx_voxelize_kernel(const VoxParams P) {
     __shared__ float4 sA[kMaxCand];   // rel x, rel y, rel z, r^2 + tau
@@ -122,6 +206,10 @@ __global__ void __launch_bounds__(kThreads) mvx_voxelize_kernel(const VoxParams 
     const int cnt = (int)bin.y;
     const uint32_t* list = P.lists + (size_t)P.mol_offsets[mol] * (size_t)P.maxcols + bin.x;
 
+    if (cnt == 0 && P.clast) {
+        zero_fill_tile_clast<es, kThreads>(out_mol, D, P.Cout, x0, y0, z0, z1, P.c_begin, P.c_end, tid);
+        return;
+    }
     if (cnt == 0) {   // empty column: pure zero fill
         float zero[NV];
 #pragma unroll
@@ -236,12 +324,19 @@ __global__ void __launch_bounds__(kThreads) mvx_voxelize_kernel(const VoxParams 
                     }
                 }
             }
-            if (valid) {
+            if (valid && !P.clast) {
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     const int ch = c0 + c;
                     if (ch < P.c_end) store_vox<O16>(out_mol + ((size_t)ch * plane + ((size_t)x * D + y) * D + z) * es, acc[c], P.out_kind);
                 }
+            } else if (valid) {   // channels-last: element stores
+#pragma unroll
+                for (int k = 0; k < NV; ++k)
+#pragma unroll
+                    for (int c = 0; c < CH; ++c)
+                        if (c0 + c < P.c_end)
+                            store_chan1<O16>(out_mol + ((((size_t)x * D + y) * D + z + k) * P.Cout + c0 + c) * es, acc[c][k], P.out_kind);
             }
         }
     }
@@ -315,7 +410,7 @@ __device__ __forceinline__ void cells_body(const VoxParams& P) {
     const int cnt = (int)bin.y;
 
     if (cnt == 0) {   // empty column: pure zero fill
-        zero_fill_tile<O16>(out_mol, plane, D, x0, y0, z0, z1, P.c_begin, P.c_end, tid);
+        zero_tile<O16, kThreads>(P, out_mol, plane, D, x0, y0, z0, z1, tid);
         return;
     }
 
@@ -524,18 +619,7 @@ __device__ __forceinline__ void cells_body(const VoxParams& P) {
                     __syncwarp();
                 }
             }
-            if (valid) {
-                char* p = out_mol + ((size_t)c0 * plane + ((size_t)x * D + y) * D + z) * es;
-                const size_t pstride = plane * es;
-                if (c0 + CH <= P.c_end) {
-#pragma unroll
-                    for (int c = 0; c < CH; ++c, p += pstride) store_vox<O16>(p, acc[c], P.out_kind);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < CH; ++c, p += pstride)
-                        if (c0 + c < P.c_end) store_vox<O16>(p, acc[c], P.out_kind);
-                }
-            }
+            if (valid) store_lane<CH, O16>(P, out_mol, plane, D, x, y, z, c0, acc);
         }
     }
 }
@@ -605,7 +689,7 @@ __device__ __forceinline__ void tiles_body(const VoxParams& P, const int tile_id
     const size_t gcol = (size_t)mol * P.ncol + col;
     const uint2 bin = P.bins[gcol];
     if (bin.y == 0) {   // empty column
-        zero_fill_tile<O16>(out_mol, plane, D, x0, y0, z0, z1, P.c_begin, P.c_end, tid);
+        zero_tile<O16, kThreads>(P, out_mol, plane, D, x0, y0, z0, z1, tid);
         return;
     }
     const int ncz_max = (P.tz + CZ - 1) / CZ;
@@ -615,7 +699,7 @@ __device__ __forceinline__ void tiles_body(const VoxParams& P, const int tile_id
     const int seg_start = (int)lb_first.x;
     const int total = (int)(lb_last.x + lb_last.y) - seg_start;   // layers of a chunk are consecutive
     if (total == 0) {   // the column has atoms, none reaches this z chunk
-        zero_fill_tile<O16>(out_mol, plane, D, x0, y0, z0, z1, P.c_begin, P.c_end, tid);
+        zero_tile<O16, kThreads>(P, out_mol, plane, D, x0, y0, z0, z1, tid);
         return;
     }
     if (tid < ncz) {
@@ -798,18 +882,7 @@ __device__ __forceinline__ void tiles_body(const VoxParams& P, const int tile_id
                     __syncwarp();
                 }
             }
-            if (valid) {
-                char* p = out_mol + ((size_t)c0 * plane + ((size_t)x * D + y) * D + z) * es;
-                const size_t pstride = plane * es;
-                if (c0 + CH <= P.c_end) {
-#pragma unroll
-                    for (int c = 0; c < CH; ++c, p += pstride) store_vox<O16>(p, acc[c], P.out_kind);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < CH; ++c, p += pstride)
-                        if (c0 + c < P.c_end) store_vox<O16>(p, acc[c], P.out_kind);
-                }
-            }
+            if (valid) store_lane<CH, O16>(P, out_mol, plane, D, x, y, z, c0, acc);
         }
     }
 }
@@ -1241,18 +1314,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
                         for (int k = 0; k < 4; ++k) acc[c][k] = 0.f;
                 };
                 auto store = [&](const int c0) {
-                    if (valid) {
-                        char* p = out_mol + ((size_t)c0 * plane + ((size_t)x * D + y) * D + z) * es;
-                        const size_t pstride = plane * es;
-                        if (c0 + CH <= P.c_end) {
-#pragma unroll
-                            for (int c = 0; c < CH; ++c, p += pstride) store_vox<O16>(p, acc[c], P.out_kind);
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < CH; ++c, p += pstride)
-                                if (c0 + c < P.c_end) store_vox<O16>(p, acc[c], P.out_kind);
-                        }
-                    }
+                    if (valid) store_lane<CH, O16>(P, out_mol, plane, D, x, y, z, c0, acc);
                 };
 
                 // When the whole layer fits one warp list (the common case) its hit masks serve every channel chunk;
@@ -1272,8 +1334,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
                 if (tid == 0) produce(false);   // keep the ring topped up without ever blocking
             }
         } else if (total == 0u) {
-            zero_fill_tile<O16, kPipeThreads>(reinterpret_cast<char*>(P.out) + (size_t)mol * P.Cout * plane * es, plane, D,
-                                              x0, y0, z0, z1, P.c_begin, P.c_end, tid);
+            zero_tile<O16, kPipeThreads>(P, reinterpret_cast<char*>(P.out) + (size_t)mol * P.Cout * plane * es, plane, D, x0, y0, z0, z1, tid);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);

@@ -77,6 +77,11 @@ class Voxelizer:
         assert out_dtype in (torch.float32, torch.bfloat16, torch.float16, torch.float64), \
             "out_dtype must be float32, bfloat16, float16 or float64"
         self.out_dtype = out_dtype
+        # channels_last=True: grids are allocated in the channels-last memory format (torch.channels_last_3d: logical shape
+        # (B, C, D, H, W), physical (B, D, H, W, C) — the layout the reference README writes its formulas in, README.md:138-142,
+        # and the one a channels-last 3-D CNN reads without a transpose).  Same values bit for bit.  An
+        # `out=` / `out_grid=` tensor decides by its own strides, whatever this default says.
+        self.channels_last = bool(kwargs.get("channels_last", False))
         # random rigid transform (random_translation / random_rotation of every forward_*): where the per-molecule
         # parameters come from.  "philox" (default): drawn on the device inside the prep kernel from a counter-based
         # generator keyed by (seed, molecule index) — molecule indices continue across calls, `rng_offset=` pins them
@@ -188,6 +193,9 @@ class Voxelizer:
         if batch_size is not None:
             shape = (batch_size,) + shape
         fn = torch.zeros if init_zero else torch.empty
+        if self.channels_last:   # physical (.., D, H, W, C), logical (.., C, D, H, W)
+            g = fn(shape[:-4] + shape[-3:] + (num_channels,), dtype=self.out_dtype, device=self.device)
+            return g.permute(0, 4, 1, 2, 3) if batch_size is not None else g.permute(3, 0, 1, 2)
         return fn(shape, dtype=self.out_dtype, device=self.device)
 
     def asarray(self, array, obj: str):
@@ -433,9 +441,12 @@ class Voxelizer:
         else:
             self._check_radii(mode, radii, N, C)
 
+        clast = self.channels_last
         if out is not None:
-            assert isinstance(out, torch.Tensor) and out.dtype == self.out_dtype and out.is_contiguous() and \
-                (out.is_cuda or not have_cuda), f"out_grid must be a contiguous {self.out_dtype} CUDA tensor"
+            assert isinstance(out, torch.Tensor) and out.ndim == 5, "out_grid must be a (C, D, H, W) / (B, C, D, H, W) tensor"
+            clast = not out.is_contiguous() and out.permute(0, 2, 3, 4, 1).is_contiguous()
+            assert out.dtype == self.out_dtype and (out.is_contiguous() or clast) and \
+                (out.is_cuda or not have_cuda), f"out_grid must be a contiguous (or channels-last) {self.out_dtype} CUDA tensor"
             if mode == "types":
                 assert out.shape[1] >= C, f"Output channel is less than number of types: {out.shape[1]} < {C}"
                 assert tuple(out.shape[2:]) == (D, D, D), \
@@ -455,7 +466,7 @@ class Voxelizer:
         if not have_cuda:
             raise RuntimeError("molvoxel_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         if out is None:
-            out = torch.empty((B, out_channels, D, D, D), dtype=self.out_dtype, device=self.device)
+            out = self.get_empty_grid(out_channels, B)
 
         # centring and the optional rigid transform stay inside the prep kernel, in numpy's promoted dtype
         # (numpy/voxelizer.py:263-265).  Explicit transforms, or parameters drawn on the host in the reference's
@@ -500,6 +511,7 @@ class Voxelizer:
         b.radius, b.max_radius = 0.0, 0.0
         b.out_dtype = _lib.OUT_DTYPE[str(self.out_dtype).replace("torch.", "")]
         b.transform_flags = tf_flags
+        b.out_layout = _lib.LAYOUT_DHWC if clast else _lib.LAYOUT_CDHW
         if tf_flags and tf_rows is None:   # device-drawn: key + global molecule index
             b.rng_seed = self._seed
             b.random_translation = float(random_translation or 0.0)
@@ -574,7 +586,7 @@ class Voxelizer:
         spec = self._spec()
         # workspace size of this call shape: cached (two C calls, each planning the batch, per forward otherwise)
         key = (mode, B, N, C, out_channels, on_device, int(b.coords_dtype), int(b.centers_dtype), int(b.features_dtype),
-               int(b.out_dtype), float(b.radius), float(b.max_radius), int(b.transform_flags), tf_rows is not None,
+               int(b.out_dtype), int(b.out_layout), float(b.radius), float(b.max_radius), int(b.transform_flags), tf_rows is not None,
                centers is None, self._radii_type, self._density_type, self.blockdim, float(self._sigma))
         total = self._ws_need.get(key)
         if total is None:

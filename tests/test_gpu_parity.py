@@ -1104,3 +1104,68 @@ def test_two_stream_form_equals_the_single_stream_form_bitwise():
     fast.forward_types_batch(dev[0][0], dev[0][1], None, torch.from_numpy(bad).cuda(), 1.0, C, inputs_ready=True)
     with pytest.raises(ValueError):
         fast.check_status()
+
+
+# ---- channels-last output (reference README.md:138-142 writes the grid channels-last) ----
+@pytest.mark.parametrize("kernel", ["cells", "tiles", "pipe", "rows"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_channels_last_output_equals_reference_layout_bitwise(kernel, dtype, monkeypatch):
+    """(B, D, H, W, C) grids hold the same values, bit for bit, as the reference's (B, C, D, H, W) layout: every kernel form,
+    types / features / single, channel counts with and without 16-byte channel groups, surplus channels, empty molecules."""
+    monkeypatch.setenv("MVX_KERNEL", kernel)
+    rng = np.random.default_rng(77)
+    offs, coords, types = ligand_batch(rng, 5, 9)
+    offs = np.concatenate([offs, offs[-1:]]).astype(np.int32)   # a trailing empty molecule: pure zero fill
+    B = offs.shape[0] - 1
+    for dim in (32, 36):
+        std = mv.create_voxelizer(0.5, dim, "scalar", "gaussian", library="b200", out_dtype=dtype)
+        cl = mv.create_voxelizer(0.5, dim, "scalar", "gaussian", library="b200", out_dtype=dtype, channels_last=True)
+        for C in (9, 12, 16):       # 9: element stores; 12 / 16: four channels per store
+            a = std.forward_types_batch(coords, offs, None, types, 1.0, C)
+            b = cl.forward_types_batch(coords, offs, None, types, 1.0, C)
+            assert tuple(b.shape) == (B, C, dim, dim, dim) and b.permute(0, 2, 3, 4, 1).is_contiguous()
+            assert b.is_contiguous(memory_format=torch.channels_last_3d)
+            assert torch.equal(a, b)
+        for C in (3, 8, 20):        # 20: two channel chunks, the second partial
+            feats = rng.uniform(size=(coords.shape[0], C)).astype(np.float32)
+            a = std.forward_features_batch(coords, offs, None, feats, 1.0)
+            b = cl.forward_features_batch(coords, offs, None, feats, 1.0)
+            assert torch.equal(a, b)
+        a = std.forward_single_batch(coords, offs, None, 1.0)
+        b = cl.forward_single_batch(coords, offs, None, 1.0)
+        assert torch.equal(a, b)
+    # the layout follows the `out` tensor, whatever the voxelizer's default: a reference-layout voxelizer fills a
+    # channels-last tensor in place, and the other way round
+    out_cl = cl.get_empty_grid(12, B)
+    r = std.forward_types_batch(coords, offs, None, types, 1.0, 9, out=out_cl)
+    assert r is out_cl and torch.equal(out_cl, std.forward_types_batch(coords, offs, None, types, 1.0, 9, out=std.get_empty_grid(12, B)))
+    assert float(out_cl[:, 9:].abs().max()) == 0.0
+    out_std = std.get_empty_grid(9, B)
+    assert cl.forward_types_batch(coords, offs, None, types, 1.0, 9, out=out_std) is out_std
+    # single-molecule reference calls: (C, D, H, W) logical shape, channels innermost in memory
+    g = cl.forward_types(coords[:offs[1]], None, types[:offs[1]], 1.0)
+    assert tuple(g.shape) == (int(types[:offs[1]].max()) + 1, 36, 36, 36) and g.permute(1, 2, 3, 0).is_contiguous()
+    assert torch.equal(g, std.forward_types(coords[:offs[1]], None, types[:offs[1]], 1.0))
+
+
+def test_channels_last_dense_pocket_channelwise_and_fp64():
+    """Channels-last through the dense (pipelined) form at a cfg2-like shape, the per-channel passes of channel-wise
+    feature radii (one channel per launch: element stores) and the precision=64 kernel."""
+    rng = np.random.default_rng(78)
+    B, V, C, dim = 3, 1800, 16, 48
+    offs = (np.arange(B + 1) * V).astype(np.int32)
+    coords = rng.uniform(-12.0, 12.0, size=(B * V, 3)).astype(np.float32).astype(np.float64)
+    feats = (rng.uniform(size=(B * V, C)) < 0.3).astype(np.float32)
+    std = mv.create_voxelizer(0.5, dim, "scalar", "gaussian", library="b200")
+    cl = mv.create_voxelizer(0.5, dim, "scalar", "gaussian", library="b200", channels_last=True)
+    assert torch.equal(std.forward_features_batch(coords, offs, None, feats, 1.0), cl.forward_features_batch(coords, offs, None, feats, 1.0))
+    radii = rng.uniform(0.8, 1.6, size=C).astype(np.float32)
+    std = mv.create_voxelizer(0.5, dim, "channel-wise", "gaussian", library="b200")
+    cl = mv.create_voxelizer(0.5, dim, "channel-wise", "gaussian", library="b200", channels_last=True)
+    assert torch.equal(std.forward_features_batch(coords[:V], offs[:2], None, feats[:V], radii),
+                       cl.forward_features_batch(coords[:V], offs[:2], None, feats[:V], radii))
+    std = mv.create_voxelizer(0.5, 20, "scalar", "binary", library="b200", precision=64)
+    cl = mv.create_voxelizer(0.5, 20, "scalar", "binary", library="b200", precision=64, channels_last=True)
+    t = rng.integers(0, 5, size=V).astype(np.int32)
+    a, b = std.forward_types(coords[:V] * 0.4, None, t, 1.0), cl.forward_types(coords[:V] * 0.4, None, t, 1.0)
+    assert b.dtype == torch.float64 and torch.equal(a, b)

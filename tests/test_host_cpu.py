@@ -67,6 +67,7 @@ def test_kernel_form_follows_atom_density(monkeypatch):
     (lambda s, b: setattr(b, "out_channels", 2), _lib.MVX_ERR_BAD_SHAPE),
     (lambda s, b: setattr(b, "radius", 0.0), _lib.MVX_ERR_BAD_SHAPE),
     (lambda s, b: setattr(b, "coords", None), _lib.MVX_ERR_NULL_POINTER),
+    (lambda s, b: setattr(b, "out_layout", 2), _lib.MVX_ERR_BAD_ENUM),
 ])
 def test_c_abi_argument_errors(mutate, code):
     L = _lib.lib()
@@ -111,6 +112,29 @@ def test_no_cpu_fallback():
         vox.forward_single(np.zeros((1, 3)), None, 1.0)
     with pytest.raises(RuntimeError):
         vox.cpu()
+
+
+def test_channels_last_argument_handling_is_host_side():
+    """The output layout is an argument of the C ABI (mvx_batch.out_layout); the Python mirror derives it from the out
+    tensor's strides and accepts exactly the two dense layouts."""
+    L = _lib.lib()
+    spec, b = _lib.GridSpec(0.5, 64, 0, 0.5, 0, 8), _batch()
+    need_a, need_b = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    assert L.mvx_workspace_bytes(ctypes.byref(spec), ctypes.byref(b), ctypes.byref(need_a)) == 0
+    b.out_layout = _lib.LAYOUT_DHWC
+    assert L.mvx_workspace_bytes(ctypes.byref(spec), ctypes.byref(b), ctypes.byref(need_b)) == 0
+    assert need_a.value == need_b.value > 0
+    assert L.mvx_compact_bricks(ctypes.byref(spec), ctypes.byref(b), None, None, None, None, 0, None, None) == _lib.MVX_ERR_UNSUPPORTED
+    vox = mv.create_voxelizer(0.5, 16, library="b200", device="cpu", channels_last=True)
+    g = vox.get_empty_grid(5, 3, init_zero=True)
+    assert tuple(g.shape) == (3, 5, 16, 16, 16) and g.is_contiguous(memory_format=torch.channels_last_3d)
+    assert tuple(vox.get_empty_grid(5).shape) == (5, 16, 16, 16) and vox.get_empty_grid(5).permute(1, 2, 3, 0).is_contiguous()
+    coords, offs, types = np.zeros((4, 3)), np.array([0, 2, 3, 4], dtype=np.int32), np.zeros(4, dtype=np.int32)
+    with pytest.raises(AssertionError, match="contiguous"):   # neither (B,C,D,H,W)- nor (B,D,H,W,C)-contiguous
+        vox.forward_types_batch(coords, offs, None, types, 1.0, 5, out=torch.zeros(3, 16, 5, 16, 16).permute(0, 2, 1, 3, 4))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):   # a channels-last out passes the checks
+            vox.forward_types_batch(coords, offs, None, types, 1.0, 5, out=g)
 
 
 def test_product_never_imports_oracle():
