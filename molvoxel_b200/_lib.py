@@ -17,7 +17,7 @@ OBJ_DIR = os.path.join(CSRC, "_obj")
 API_SOURCE = os.path.join(CSRC, "mvx_api.cu")
 INST_SOURCE = os.path.join(CSRC, "mvx_vox_inst.cu")
 SOURCES = [API_SOURCE, INST_SOURCE]
-HEADERS = [os.path.join(CSRC, h) for h in ("mvx_common.cuh", "mvx_rigid.cuh", "mvx_bin_kernels.cuh", "mvx_vox_kernels.cuh", "mvx_launch.cuh")] + \
+HEADERS = [os.path.join(CSRC, h) for h in ("mvx_common.cuh", "mvx_rigid.cuh", "mvx_bin_kernels.cuh", "mvx_vox_kernels.cuh", "mvx_vox_ws.cuh", "mvx_launch.cuh")] + \
           [os.path.join(os.path.dirname(_HERE), "include", "molvoxel_b200.h")]
 # (mode, channel chunk) pairs the voxelize kernels are instantiated for (x binary / gaussian): mvx_api.cu:launch_vox
 INSTANCES = [(0, 1)] + [(m, ch) for m in (1, 2) for ch in (1, 4, 8, 12, 16)]
@@ -115,7 +115,8 @@ def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
         fcntl.flock(lock, fcntl.LOCK_EX)
         if not force and not _stale():   # another process built it while this one waited
             return SO_PATH
-        flags = NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+        # MVX_NVCC_FLAGS: extra flags of an experimental build (e.g. -DMVX_WITH_WS together with MVX_SO=<other path>)
+        flags = NVCC_FLAGS + list(extra_flags) + os.environ.get("MVX_NVCC_FLAGS", "").split() + (["-Xptxas", "-v"] if verbose else [])
         jobs = [([nvcc] + flags + ["-c", API_SOURCE, "-o", os.path.join(OBJ_DIR, "mvx_api.o")])]
         for mode, ch in INSTANCES:
             for binary in (0, 1):

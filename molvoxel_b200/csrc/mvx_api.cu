@@ -58,6 +58,7 @@ struct Plan {
     int pipe_sc;   // pipelined form: largest tile (entries) it takes
     int pipe_q;    // ... float4 words of its shared-memory ring
     bool pipe_multi;   // ... with the hit-weight cache (several channel chunks per cell)
+    int ws_nb;         // ... warp-specialised: list-builder warps (0 = the classic form)
 };
 
 int check_args(const mvx_grid_spec* s, const mvx_batch* b) {
@@ -234,6 +235,16 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
         // several channel chunks per cell: the pipelined kernel caches the hit weights, its ring is smaller
         pl->pipe_multi = pick_chunk(b->mode, b->out_channels) == 16 && b->out_channels > 16;
         pl->pipe_q = mvx::pipe_ring_q(pl->pipe_multi);
+        pl->ws_nb = 0;
+#ifdef MVX_WITH_WS   // experiment build: the warp-specialised variant (mvx_vox_ws.cuh)
+        if (pl->form == FORM_PIPE && b->mode == MVX_MODE_FEATURES && pick_chunk(b->mode, b->out_channels) == 16) {
+            if (const char* e = std::getenv("MVX_WS")) {   // experiments: 4 | 8 list-builder warps
+                const int v = std::atoi(e);
+                if (v == 4 || v == 8 || v == 20) pl->ws_nb = v;
+            }
+            if (pl->ws_nb) pl->pipe_q = mvx::ws_ring_q(mvx::ws_builders(pl->ws_nb), mvx::ws_walkers(pl->ws_nb), pl->pipe_multi);
+        }
+#endif
         pl->pipe_sc = pl->pipe_q / 2 / pl->es4;   // the pipelined form takes tiles up to half its ring
     }
     pl->off_alayers = off;  off += align_up(layered(pl->form) ? N * sizeof(uint32_t) : 0);
@@ -477,7 +488,7 @@ int enqueue(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, void* 
         vp.lent = (const float4*)(ws + pl.off_lent);
         vp.lbins = (const uint2*)(ws + pl.off_lbins);
         vp.tdesc = pl.form == FORM_PIPE ? (const mvx::TileDesc*)(ws + pl.off_tdesc) : nullptr;
-        vp.pipe_sc = pl.pipe_sc; vp.pipe_q = pl.pipe_q;
+        vp.pipe_sc = pl.pipe_sc; vp.pipe_q = pl.pipe_q; vp.ws_nb = pl.ws_nb;
         const unsigned long long nblk = (unsigned long long)B * pl.ncol * pl.nzc;
         if (nblk > 0x7fffffffULL) return fail(MVX_ERR_BAD_SHAPE, "batch too large for one launch; split it");
         const bool binary = spec->density_type == MVX_DENSITY_BINARY;

@@ -150,6 +150,7 @@ struct VoxParams {
     const TileDesc* tdesc;     // pipelined form; for the tile form: non-null = only tiles with more than pipe_sc entries
     int pipe_sc;               // pipelined form: largest tile (entries) it takes; larger ones go to the tile form
     int pipe_q;                // pipelined form: float4 words of the shared-memory entry ring
+    int ws_nb;                 // pipelined form: 0 = every warp does whole cells; 4 | 8 | 20 = warp-specialised (see ws_builders / ws_walkers)
     int lean;                  // cells form: the register-capped instance (the next batch's binning shares the SMs)
     void* out;                 // (B, Cout, D, D, D), element type by out_kind
     int out_kind;              // 0 fp32 (reference), 1 bf16, 2 fp16 (reduced-precision output)
@@ -175,5 +176,20 @@ constexpr int kPipeFixedBytes = kPipeSlots * ((int)sizeof(TileDesc) + 3 * 8 + 2 
 constexpr int kPipeHitCache = 12;
 constexpr int kPipeCacheBytes = kPipeWarps * kPipeHitCache * 32 * ((int)sizeof(float4) + (int)sizeof(uint32_t));
 constexpr int pipe_ring_q(bool multi) { return (kPipeSmemBytes - kPipeFixedBytes - (multi ? kPipeCacheBytes : 0)) / 16; }
+
+
+// ---- warp-specialised pipelined form: NB list-builder warps (few registers: cell filter + near test) hand
+// (entry indices, per-lane hit masks) through a shared-memory job ring to NWK accumulator warps (many registers: hit walk + stores)
+constexpr int kWsJobs = 32;                                   // slots of the job ring (a power of two)
+constexpr int kWsList = 128;                                  // list capacity of a job (four 32-bit hit masks per lane)
+constexpr int kWsJobBytes = 16 + kWsList * 2 + 32 * 16;       // header, entry indices (u16), hit masks (16 B per lane)
+constexpr int ws_fixed_bytes(int nb) {   // tile slots (descriptor, 3 barriers, 3 words), tickets, job ring (+ full barrier, generation), builder lists
+    return kPipeSlots * ((int)sizeof(TileDesc) + 3 * 8 + 3 * 4) + 32 + kWsJobs * (kWsJobBytes + 16) + nb * kWsList * (int)sizeof(float4);
+}
+constexpr int ws_cache_bytes(int nwk) { return nwk * kPipeHitCache * 32 * ((int)sizeof(float4) + (int)sizeof(uint32_t)); }
+constexpr int ws_ring_q(int nb, int nwk, bool multi) { return (kPipeSmemBytes - ws_fixed_bytes(nb) - (multi ? ws_cache_bytes(nwk) : 0)) / 16; }
+// role split by the experiment knob MVX_WS / VoxParams::ws_nb: 4 -> 4 + 12 warps, 8 -> 8 + 8, 20 -> 8 + 12 (640 threads)
+constexpr int ws_builders(int knob) { return knob == 4 ? 4 : 8; }
+constexpr int ws_walkers(int knob) { return knob == 8 ? 8 : 12; }
 
 }  // namespace mvx

@@ -3,6 +3,9 @@
 // (molvoxel_b200/_lib.py compiles this file once per combination, in parallel, and links the objects with mvx_api.o).
 #include "mvx_launch.cuh"
 #include "mvx_vox_kernels.cuh"
+#ifdef MVX_WITH_WS
+#include "mvx_vox_ws.cuh"
+#endif
 
 namespace mvx {
 namespace {
@@ -29,14 +32,35 @@ cudaError_t launch_form_out(const VoxParams& vp, int form, int nv, unsigned grid
         static DeviceSet cfg, cfg_m, cfg_t;
         unsigned pg = 0;
         if (pipe_grid(grid, &pg) != 0) return cudaErrorInvalidDevice;
+        bool ws_done = false;
+#ifdef MVX_WITH_WS
+        if constexpr (MODE == 2 && CH == 16) {   // warp-specialised instance (list-builder + accumulator warps)
+            if (vp.ws_nb == 4 || vp.ws_nb == 8 || vp.ws_nb == 20) {
+                static DeviceSet cfg_w[6];
+                const bool multi = vp.pipe_q == ws_ring_q(ws_builders(vp.ws_nb), ws_walkers(vp.ws_nb), true);
+                cudaError_t ew = cudaSuccess;
+#define MVX_WS_LAUNCH(SLOT, MULTI_, NB_, NWK_, RB_, RW_)                                                                              \
+    {                                                                                                                                \
+        ew = set_smem(mvx_voxelize_ws_kernel<MODE, CH, BINARY, O16, MULTI_, NB_, NWK_, RB_, RW_>, smem, &cfg_w[SLOT]);                \
+        if (ew == cudaSuccess) mvx_voxelize_ws_kernel<MODE, CH, BINARY, O16, MULTI_, NB_, NWK_, RB_, RW_><<<pg, (NB_ + NWK_) * 32, smem, st>>>(vp, grid); \
+    }
+                if (vp.ws_nb == 4) { if (multi) MVX_WS_LAUNCH(0, true, 4, 12, 56, 152) else MVX_WS_LAUNCH(1, false, 4, 12, 56, 152) }
+                else if (vp.ws_nb == 8) { if (multi) MVX_WS_LAUNCH(2, true, 8, 8, 64, 192) else MVX_WS_LAUNCH(3, false, 8, 8, 64, 192) }
+                else { if (multi) MVX_WS_LAUNCH(4, true, 8, 12, 48, 128) else MVX_WS_LAUNCH(5, false, 8, 12, 48, 128) }
+#undef MVX_WS_LAUNCH
+                if (ew != cudaSuccess) return ew;
+                ws_done = true;
+            }
+        }
+#endif
         if constexpr (CH == 16) {   // several channel chunks per cell (C > 16): hit-weight cache
-            if (vp.pipe_q == pipe_ring_q(true)) {
+            if (!ws_done && vp.pipe_q == pipe_ring_q(true)) {
                 cudaError_t em = set_smem(mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, true>, smem, &cfg_m);
                 if (em != cudaSuccess) return em;
                 mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, true><<<pg, kPipeThreads, smem, st>>>(vp, grid);
             }
         }
-        if (CH != 16 || vp.pipe_q != pipe_ring_q(true)) {
+        if (!ws_done && (CH != 16 || vp.pipe_q != pipe_ring_q(true))) {
             cudaError_t em = set_smem(mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, false>, smem, &cfg);
             if (em != cudaSuccess) return em;
             mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, false><<<pg, kPipeThreads, smem, st>>>(vp, grid);

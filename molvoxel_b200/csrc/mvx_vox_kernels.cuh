@@ -972,6 +972,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   //
 }
 // Bounded wait: a pipeline bug traps (the launch fails with an error) instead of hanging the GPU.  The bound is wall
 // time (20 s on %globaltimer, looked at every 4096 failed attempts), so time-slicing with other contexts cannot trip it.
+template <int TAG>
 static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
     unsigned long long t0, t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -983,8 +984,11 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parit
         }
     }
 }
+// TAG: one copy of the out-of-line slow path per register-budget region of a warp-specialised kernel (a function shared by
+// callers under different setmaxnreg budgets makes ptxas' register allocation fail)
+template <int TAG = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow<TAG>(bar, parity);
 }
 // global -> shared bulk copy (bytes % 16 == 0, both addresses 16-byte aligned); completion counts on `bar`
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
