@@ -98,23 +98,74 @@ __device__ __forceinline__ void zero_fill_tile(char* out_mol, size_t plane, int 
 }
 
 // ---- channels-last output (B, D, H, W, Cout), SURVEY row f3: the Cout channels of one voxel are contiguous ----
+// Plain (write-back) stores: a 32-byte sector of a channels-last voxel is completed by consecutive store instructions,
+// so the lines should stay in L2 until they are whole (the streaming hint of the reference-layout stores evicts first).
 template <bool O16>
 __device__ __forceinline__ void store_chan1(char* p, float v, int kind) {
-    if (!O16) __stcs(reinterpret_cast<float*>(p), v);
+    if (!O16) *reinterpret_cast<float*>(p) = v;
     else if (kind == 1) *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16_rn(v);
     else *reinterpret_cast<__half*>(p) = __float2half_rn(v);
 }
 template <bool O16>
-__device__ __forceinline__ void store_chan4(char* p, float a, float b, float c, float d, int kind) {
-    const float v[4] = {a, b, c, d};
-    store_vox<O16>(p, v, kind);   // four consecutive channels of one voxel: one 16-byte (fp32) / 8-byte (16-bit) store
+__device__ __forceinline__ void store_chan4(char* p, float a, float b, float c, float d, int kind) {   // four consecutive channels of one voxel
+    if (!O16) {
+        *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+    } else if (kind == 1) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+        *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    } else {
+        const __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+        *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
 }
-// One lane's CH channels x 4 z voxels -> out, either layout.  (x, y, z) is the lane's first voxel, c0 the chunk's first channel.
+// Channels-last stores of a lane PAIR (lanes l, l ^ 1: z neighbours of one (x, y) row).  Each lane holds NQ chunks of 4
+// consecutive elements (a chunk = 16 B fp32 / 8 B 16-bit), contiguous from its base address; the partner's run starts
+// `pdelta` bytes away.  Adjacent chunks (2j, 2j + 1) of ONE lane are written by the two lanes in the same instruction —
+// the even lane's pair first, then the odd lane's — so a store instruction fills whole 32-byte sectors instead of
+// halves (one shuffle per element moves the other half across).  Must be called by the whole warp.
+template <int NQ, bool O16>
+__device__ __forceinline__ void store_chunk_pairs(char* p, const ptrdiff_t pdelta, const bool valid, const bool odd,
+                                                  const float (&v)[NQ][4], const int kind) {
+    constexpr int CB = O16 ? 8 : 16;
+    const bool pvalid = __shfl_xor_sync(0xffffffffu, valid ? 1 : 0, 1) != 0;
+    const bool valid_even = odd ? pvalid : valid, valid_odd = odd ? valid : pvalid;
+    char* const pp = p + pdelta;
+#pragma unroll
+    for (int j = 0; j + 1 < NQ; j += 2) {
+        float r[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r[e] = __shfl_xor_sync(0xffffffffu, odd ? v[j][e] : v[j + 1][e], 1);
+        if (valid_even) {   // the even lane's chunks 2j, 2j + 1
+            if (odd) store_chan4<O16>(pp + (j + 1) * CB, r[0], r[1], r[2], r[3], kind);
+            else store_chan4<O16>(p + j * CB, v[j][0], v[j][1], v[j][2], v[j][3], kind);
+        }
+        if (valid_odd) {    // the odd lane's chunks 2j, 2j + 1
+            if (odd) store_chan4<O16>(p + (j + 1) * CB, v[j + 1][0], v[j + 1][1], v[j + 1][2], v[j + 1][3], kind);
+            else store_chan4<O16>(pp + j * CB, r[0], r[1], r[2], r[3], kind);
+        }
+    }
+    if ((NQ & 1) && valid) store_chan4<O16>(p + (NQ - 1) * CB, v[NQ - 1][0], v[NQ - 1][1], v[NQ - 1][2], v[NQ - 1][3], kind);
+}
+// A lane's 4 voxels x COUT channels are 4 * COUT consecutive elements in the channels-last layout when one channel chunk
+// covers the grid: written as COUT 4-element chunks whatever COUT is (register order fixed at compile time).
+template <int CH, int COUT, bool O16>
+__device__ __forceinline__ void store_lane_flat(char* p, const ptrdiff_t pdelta, const bool valid, const bool odd,
+                                                const float (&acc)[CH][4], const int kind) {
+    float v[COUT][4];
+#pragma unroll
+    for (int q = 0; q < COUT; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[q][e] = acc[(4 * q + e) % COUT][(4 * q + e) / COUT];
+    store_chunk_pairs<COUT, O16>(p, pdelta, valid, odd, v, kind);
+}
+// One lane's CH channels x 4 z voxels -> out, either layout.  (x, y, z) is the lane's first voxel, c0 the chunk's first
+// channel.  Called by the whole warp (the channels-last forms exchange data between lanes); `valid`: this lane's voxels exist.
 template <int CH, bool O16>
 __device__ __forceinline__ void store_lane(const VoxParams& P, char* out_mol, size_t plane, int D, int x, int y, int z,
-                                           int c0, const float (&acc)[CH][4]) {
+                                           int c0, const float (&acc)[CH][4], const bool valid) {
     constexpr int es = O16 ? 2 : 4;
     if (!P.clast) {
+        if (!valid) return;
         char* p = out_mol + ((size_t)c0 * plane + ((size_t)x * D + y) * D + z) * es;
         const size_t pstride = plane * es;
         if (c0 + CH <= P.c_end) {
@@ -129,17 +180,36 @@ __device__ __forceinline__ void store_lane(const VoxParams& P, char* out_mol, si
     }
     const size_t vstride = (size_t)P.Cout * es;
     char* p = out_mol + (((size_t)x * D + y) * D + z) * vstride + (size_t)c0 * es;
-    const bool vec = CH % 4 == 0 && (P.Cout & 3) == 0 && (c0 & 3) == 0 && c0 + CH <= P.c_end;
+    const bool odd = (threadIdx.x & 1u) != 0u;   // lane = row * 4 + zq: the partner lane holds the next / previous 4 z voxels
+    const ptrdiff_t pdelta = odd ? -(ptrdiff_t)(4 * vstride) : (ptrdiff_t)(4 * vstride);
+    const bool whole = c0 == 0 && P.c_begin == 0 && P.c_end == P.Cout;   // one channel chunk covers the grid
+    if (CH >= 4 && whole && P.Cout <= CH && P.Cout > CH - 4) {   // warp-uniform
+        switch (CH - P.Cout) {
+            case 0: store_lane_flat<CH, CH, O16>(p, pdelta, valid, odd, acc, P.out_kind); break;
+            case 1: store_lane_flat<CH, (CH > 1 ? CH - 1 : 1), O16>(p, pdelta, valid, odd, acc, P.out_kind); break;
+            case 2: store_lane_flat<CH, (CH > 2 ? CH - 2 : 1), O16>(p, pdelta, valid, odd, acc, P.out_kind); break;
+            default: store_lane_flat<CH, (CH > 3 ? CH - 3 : 1), O16>(p, pdelta, valid, odd, acc, P.out_kind); break;
+        }
+        return;
+    }
+    if (CH % 4 == 0 && (P.Cout & 3) == 0 && (c0 & 3) == 0 && c0 + CH <= P.c_end) {   // warp-uniform: 4-channel chunks per voxel
+#pragma unroll
+        for (int k = 0; k < 4; ++k, p += vstride) {
+            float v[CH / 4 > 0 ? CH / 4 : 1][4];
+#pragma unroll
+            for (int q = 0; q < CH / 4; ++q)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[q][e] = acc[4 * q + e][k];
+            store_chunk_pairs<(CH / 4 > 0 ? CH / 4 : 1), O16>(p, pdelta, valid, odd, v, P.out_kind);
+        }
+        return;
+    }
+    if (!valid) return;
 #pragma unroll
     for (int k = 0; k < 4; ++k, p += vstride) {
-        if (CH % 4 == 0 && vec) {
 #pragma unroll
-            for (int c = 0; c + 3 < CH; c += 4) store_chan4<O16>(p + c * es, acc[c][k], acc[c + 1][k], acc[c + 2][k], acc[c + 3][k], P.out_kind);
-        } else {
-#pragma unroll
-            for (int c = 0; c < CH; ++c)
-                if (c0 + c < P.c_end) store_chan1<O16>(p + c * es, acc[c][k], P.out_kind);
-        }
+        for (int c = 0; c < CH; ++c)
+            if (c0 + c < P.c_end) store_chan1<O16>(p + c * es, acc[c][k], P.out_kind);
     }
 }
 // Zero fill of one tile in the channels-last layout: per (x, y) row the z range x all channels is one contiguous run.
@@ -619,7 +689,7 @@ __device__ __forceinline__ void cells_body(const VoxParams& P) {
                     __syncwarp();
                 }
             }
-            if (valid) store_lane<CH, O16>(P, out_mol, plane, D, x, y, z, c0, acc);
+            store_lane<CH, O16>(P, out_mol, plane, D, x, y, z, c0, acc, valid);
         }
     }
 }
@@ -882,7 +952,7 @@ __device__ __forceinline__ void tiles_body(const VoxParams& P, const int tile_id
                     __syncwarp();
                 }
             }
-            if (valid) store_lane<CH, O16>(P, out_mol, plane, D, x, y, z, c0, acc);
+            store_lane<CH, O16>(P, out_mol, plane, D, x, y, z, c0, acc, valid);
         }
     }
 }
@@ -1318,7 +1388,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
                         for (int k = 0; k < 4; ++k) acc[c][k] = 0.f;
                 };
                 auto store = [&](const int c0) {
-                    if (valid) store_lane<CH, O16>(P, out_mol, plane, D, x, y, z, c0, acc);
+                    store_lane<CH, O16>(P, out_mol, plane, D, x, y, z, c0, acc, valid);
                 };
 
                 // When the whole layer fits one warp list (the common case) its hit masks serve every channel chunk;

@@ -453,7 +453,7 @@ __global__ void __launch_bounds__((NB + NWK) * 32, 1) mvx_voxelize_ws_kernel(con
                 }
                 walk(hm0, hm1, hm2, hm3, c0);
             }
-            if (valid) store_lane<CH, O16>(P, out_mol, plane, D, x, y, z, c0, acc);
+            store_lane<CH, O16>(P, out_mol, plane, D, x, y, z, c0, acc, valid);
         }
         __syncwarp();
         if (lane == 0) {
