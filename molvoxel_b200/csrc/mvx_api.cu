@@ -240,7 +240,7 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
         if (pl->form == FORM_PIPE && b->mode == MVX_MODE_FEATURES && pick_chunk(b->mode, b->out_channels) == 16) {
             if (const char* e = std::getenv("MVX_WS")) {   // experiments: 4 | 8 list-builder warps
                 const int v = std::atoi(e);
-                if (v == 4 || v == 8 || v == 20) pl->ws_nb = v;
+                if ((v == 4 || v == 8 || v == 20) && b->out_layout == MVX_LAYOUT_CDHW) pl->ws_nb = v;
             }
             if (pl->ws_nb) pl->pipe_q = mvx::ws_ring_q(mvx::ws_builders(pl->ws_nb), mvx::ws_walkers(pl->ws_nb), pl->pipe_multi);
         }

@@ -25,7 +25,7 @@ static int pipe_grid(unsigned ntiles, unsigned* grid) {
     return 0;
 }
 
-template <int MODE, int CH, bool BINARY, bool O16>
+template <int MODE, int CH, bool BINARY, bool O16, bool CL>
 cudaError_t launch_form_out(const VoxParams& vp, int form, int nv, unsigned grid, cudaStream_t st) {
     if (form == FORM_PIPE) {
         constexpr size_t smem = kPipeSmemBytes;
@@ -55,45 +55,45 @@ cudaError_t launch_form_out(const VoxParams& vp, int form, int nv, unsigned grid
 #endif
         if constexpr (CH == 16) {   // several channel chunks per cell (C > 16): hit-weight cache
             if (!ws_done && vp.pipe_q == pipe_ring_q(true)) {
-                cudaError_t em = set_smem(mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, true>, smem, &cfg_m);
+                cudaError_t em = set_smem(mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, true, CL>, smem, &cfg_m);
                 if (em != cudaSuccess) return em;
-                mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, true><<<pg, kPipeThreads, smem, st>>>(vp, grid);
+                mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, true, CL><<<pg, kPipeThreads, smem, st>>>(vp, grid);
             }
         }
         if (!ws_done && (CH != 16 || vp.pipe_q != pipe_ring_q(true))) {
-            cudaError_t em = set_smem(mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, false>, smem, &cfg);
+            cudaError_t em = set_smem(mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, false, CL>, smem, &cfg);
             if (em != cudaSuccess) return em;
-            mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, false><<<pg, kPipeThreads, smem, st>>>(vp, grid);
+            mvx_voxelize_pipe_kernel<MODE, CH, BINARY, O16, false, CL><<<pg, kPipeThreads, smem, st>>>(vp, grid);
         }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         // tiles with more entries than the pipelined form takes (usually none): a small scanning grid
         constexpr size_t smem_t = tiles_smem_bytes<MODE>();
-        e = set_smem(mvx_voxelize_sweep_kernel<MODE, CH, BINARY, O16>, smem_t, &cfg_t);
+        e = set_smem(mvx_voxelize_sweep_kernel<MODE, CH, BINARY, O16, CL>, smem_t, &cfg_t);
         if (e != cudaSuccess) return e;
-        mvx_voxelize_sweep_kernel<MODE, CH, BINARY, O16><<<2 * pg < grid ? 2 * pg : grid, kThreads, smem_t, st>>>(vp, grid);
+        mvx_voxelize_sweep_kernel<MODE, CH, BINARY, O16, CL><<<2 * pg < grid ? 2 * pg : grid, kThreads, smem_t, st>>>(vp, grid);
     } else if (form == FORM_TILES) {
         constexpr size_t smem = tiles_smem_bytes<MODE>();
         static DeviceSet cfg;
-        { cudaError_t e = set_smem(mvx_voxelize_tiles_kernel<MODE, CH, BINARY, O16>, smem, &cfg); if (e != cudaSuccess) return e; }
-        mvx_voxelize_tiles_kernel<MODE, CH, BINARY, O16><<<grid, kThreads, smem, st>>>(vp);
+        { cudaError_t e = set_smem(mvx_voxelize_tiles_kernel<MODE, CH, BINARY, O16, CL>, smem, &cfg); if (e != cudaSuccess) return e; }
+        mvx_voxelize_tiles_kernel<MODE, CH, BINARY, O16, CL><<<grid, kThreads, smem, st>>>(vp);
     } else if (form == FORM_CELLS) {
         constexpr size_t smem = cells_smem_bytes<MODE, CH>();
         static DeviceSet cfg;
         if constexpr (MODE == 1 && CH >= 12) {
             if (vp.lean) {
                 static DeviceSet cfg_l;
-                { cudaError_t e = set_smem(mvx_voxelize_cells_lean_kernel<MODE, CH, BINARY, O16>, smem, &cfg_l); if (e != cudaSuccess) return e; }
-                mvx_voxelize_cells_lean_kernel<MODE, CH, BINARY, O16><<<grid, kThreads, smem, st>>>(vp);
+                { cudaError_t e = set_smem(mvx_voxelize_cells_lean_kernel<MODE, CH, BINARY, O16, CL>, smem, &cfg_l); if (e != cudaSuccess) return e; }
+                mvx_voxelize_cells_lean_kernel<MODE, CH, BINARY, O16, CL><<<grid, kThreads, smem, st>>>(vp);
                 return cudaGetLastError();
             }
         }
-        { cudaError_t e = set_smem(mvx_voxelize_cells_kernel<MODE, CH, BINARY, O16>, smem, &cfg); if (e != cudaSuccess) return e; }
-        mvx_voxelize_cells_kernel<MODE, CH, BINARY, O16><<<grid, kThreads, smem, st>>>(vp);
+        { cudaError_t e = set_smem(mvx_voxelize_cells_kernel<MODE, CH, BINARY, O16, CL>, smem, &cfg); if (e != cudaSuccess) return e; }
+        mvx_voxelize_cells_kernel<MODE, CH, BINARY, O16, CL><<<grid, kThreads, smem, st>>>(vp);
     } else if (nv == 4) {
-        mvx_voxelize_kernel<MODE, CH, BINARY, 4, O16><<<grid, kThreads, 0, st>>>(vp);
+        mvx_voxelize_kernel<MODE, CH, BINARY, 4, O16, CL><<<grid, kThreads, 0, st>>>(vp);
     } else {
-        mvx_voxelize_kernel<MODE, CH, BINARY, 1, O16><<<grid, kThreads, 0, st>>>(vp);
+        mvx_voxelize_kernel<MODE, CH, BINARY, 1, O16, CL><<<grid, kThreads, 0, st>>>(vp);
     }
     return cudaGetLastError();
 }
@@ -102,8 +102,11 @@ cudaError_t launch_form_out(const VoxParams& vp, int form, int nv, unsigned grid
 
 template <int MODE, int CH, bool BINARY>
 cudaError_t launch_form(const VoxParams& vp, int form, int nv, unsigned grid, cudaStream_t st) {
-    return vp.out_kind == 0 ? launch_form_out<MODE, CH, BINARY, false>(vp, form, nv, grid, st)
-                            : launch_form_out<MODE, CH, BINARY, true>(vp, form, nv, grid, st);
+    if (vp.clast)   // channels-last instances: the same kernels with the other store / zero-fill code
+        return vp.out_kind == 0 ? launch_form_out<MODE, CH, BINARY, false, true>(vp, form, nv, grid, st)
+                                : launch_form_out<MODE, CH, BINARY, true, true>(vp, form, nv, grid, st);
+    return vp.out_kind == 0 ? launch_form_out<MODE, CH, BINARY, false, false>(vp, form, nv, grid, st)
+                            : launch_form_out<MODE, CH, BINARY, true, false>(vp, form, nv, grid, st);
 }
 
 template cudaError_t launch_form<MVX_INST_MODE, MVX_INST_CH, (MVX_INST_BINARY != 0)>(const VoxParams&, int, int, unsigned, cudaStream_t);

@@ -160,11 +160,11 @@ __device__ __forceinline__ void store_lane_flat(char* p, const ptrdiff_t pdelta,
 }
 // One lane's CH channels x 4 z voxels -> out, either layout.  (x, y, z) is the lane's first voxel, c0 the chunk's first
 // channel.  Called by the whole warp (the channels-last forms exchange data between lanes); `valid`: this lane's voxels exist.
-template <int CH, bool O16>
+template <int CH, bool O16, bool CL>
 __device__ __forceinline__ void store_lane(const VoxParams& P, char* out_mol, size_t plane, int D, int x, int y, int z,
                                            int c0, const float (&acc)[CH][4], const bool valid) {
     constexpr int es = O16 ? 2 : 4;
-    if (!P.clast) {
+    if (!CL) {   // compile-time: the reference layout's instances carry none of the channels-last code
         if (!valid) return;
         char* p = out_mol + ((size_t)c0 * plane + ((size_t)x * D + y) * D + z) * es;
         const size_t pstride = plane * es;
@@ -245,13 +245,13 @@ __device__ __forceinline__ void zero_fill_tile_clast(char* out_mol, int D, int C
     }
 }
 // Zero fill of a tile, either layout.
-template <bool O16, int NT>
+template <bool O16, int NT, bool CL>
 __device__ __forceinline__ void zero_tile(const VoxParams& P, char* out_mol, size_t plane, int D, int x0, int y0, int z0, int z1, int tid) {
-    if (!P.clast) zero_fill_tile<O16, NT>(out_mol, plane, D, x0, y0, z0, z1, P.c_begin, P.c_end, tid);
+    if (!CL) zero_fill_tile<O16, NT>(out_mol, plane, D, x0, y0, z0, z1, P.c_begin, P.c_end, tid);
     else zero_fill_tile_clast<(O16 ? 2 : 4), NT>(out_mol, D, P.Cout, x0, y0, z0, z1, P.c_begin, P.c_end, tid);
 }
 
-template <int MODE, int CH, bool BINARY, int NV, bool O16>
+template <int MODE, int CH, bool BINARY, int NV, bool O16, bool CL>
 __global__ void __launch_bounds__(kThreads) mvx_voxelize_kernel(const VoxParams P) {
     __shared__ float4 sA[kMaxCand];   // rel x, rel y, rel z, r^2 + tau
     __shared__ float4 sB[kMaxCand];   // r^2 - tau, gaussian coefficient, forbidden planes, type | radius
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kThreads) mvx_voxelize_kernel(const VoxParams 
     const int cnt = (int)bin.y;
     const uint32_t* list = P.lists + (size_t)P.mol_offsets[mol] * (size_t)P.maxcols + bin.x;
 
-    if (cnt == 0 && P.clast) {
+    if (cnt == 0 && CL) {
         zero_fill_tile_clast<es, kThreads>(out_mol, D, P.Cout, x0, y0, z0, z1, P.c_begin, P.c_end, tid);
         return;
     }
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(kThreads) mvx_voxelize_kernel(const VoxParams 
                     }
                 }
             }
-            if (valid && !P.clast) {
+            if (valid && !CL) {
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     const int ch = c0 + c;
@@ -440,7 +440,7 @@ constexpr size_t cells_smem_bytes() {
            (MODE == 2 ? (size_t)(2 * NT) * feat_stride<CH>() * sizeof(float) : 0);
 }
 
-template <int MODE, int CH, bool BINARY, bool O16>
+template <int MODE, int CH, bool BINARY, bool O16, bool CL>
 __device__ __forceinline__ void cells_body(const VoxParams& P) {
     constexpr int NT = kThreads, LPR = 4;   // 4 lanes (one float4 each) along z per row: cells of 2 x 4 x 16 voxels
     constexpr int NW = NT / 32;             // warps per CTA
@@ -480,7 +480,7 @@ __device__ __forceinline__ void cells_body(const VoxParams& P) {
     const int cnt = (int)bin.y;
 
     if (cnt == 0) {   // empty column: pure zero fill
-        zero_tile<O16, kThreads>(P, out_mol, plane, D, x0, y0, z0, z1, tid);
+        zero_tile<O16, kThreads, CL>(P, out_mol, plane, D, x0, y0, z0, z1, tid);
         return;
     }
 
@@ -689,23 +689,23 @@ __device__ __forceinline__ void cells_body(const VoxParams& P) {
                     __syncwarp();
                 }
             }
-            store_lane<CH, O16>(P, out_mol, plane, D, x, y, z, c0, acc, valid);
+            store_lane<CH, O16, CL>(P, out_mol, plane, D, x, y, z, c0, acc, valid);
         }
     }
 }
 
 
-template <int MODE, int CH, bool BINARY, bool O16>
+template <int MODE, int CH, bool BINARY, bool O16, bool CL>
 __global__ void __launch_bounds__(kThreads, (CH <= 8 ? 3 : 2)) mvx_voxelize_cells_kernel(const VoxParams P) {
-    cells_body<MODE, CH, BINARY, O16>(P);
+    cells_body<MODE, CH, BINARY, O16, CL>(P);
 }
 
 // The same kernel capped at 112 registers: two CTAs leave 8 192 registers of an SM free, room for one 128-thread CTA of
 // the per-atom prep / binning kernels of the NEXT batch (mvx_voxelize_split: they run on a second stream in the shadow of
 // this HBM-bound kernel).  Costs a 24-byte spill, which a write-bound kernel does not notice.
-template <int MODE, int CH, bool BINARY, bool O16>
+template <int MODE, int CH, bool BINARY, bool O16, bool CL>
 __global__ void __maxnreg__(112) mvx_voxelize_cells_lean_kernel(const VoxParams P) {
-    cells_body<MODE, CH, BINARY, O16>(P);
+    cells_body<MODE, CH, BINARY, O16, CL>(P);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -730,7 +730,7 @@ constexpr size_t tiles_smem_bytes() {
            (kThreads / 32) * kWarpList * (2 * sizeof(float4) + sizeof(uint16_t));
 }
 
-template <int MODE, int CH, bool BINARY, bool O16>
+template <int MODE, int CH, bool BINARY, bool O16, bool CL>
 __device__ __forceinline__ void tiles_body(const VoxParams& P, const int tile_id) {
     constexpr int LPR = 4, RX = kCellX, RY = kCellY, CZ = kCellZ;
     constexpr int NCY = kTile / RY;
@@ -759,7 +759,7 @@ __device__ __forceinline__ void tiles_body(const VoxParams& P, const int tile_id
     const size_t gcol = (size_t)mol * P.ncol + col;
     const uint2 bin = P.bins[gcol];
     if (bin.y == 0) {   // empty column
-        zero_tile<O16, kThreads>(P, out_mol, plane, D, x0, y0, z0, z1, tid);
+        zero_tile<O16, kThreads, CL>(P, out_mol, plane, D, x0, y0, z0, z1, tid);
         return;
     }
     const int ncz_max = (P.tz + CZ - 1) / CZ;
@@ -769,7 +769,7 @@ __device__ __forceinline__ void tiles_body(const VoxParams& P, const int tile_id
     const int seg_start = (int)lb_first.x;
     const int total = (int)(lb_last.x + lb_last.y) - seg_start;   // layers of a chunk are consecutive
     if (total == 0) {   // the column has atoms, none reaches this z chunk
-        zero_tile<O16, kThreads>(P, out_mol, plane, D, x0, y0, z0, z1, tid);
+        zero_tile<O16, kThreads, CL>(P, out_mol, plane, D, x0, y0, z0, z1, tid);
         return;
     }
     if (tid < ncz) {
@@ -952,20 +952,20 @@ __device__ __forceinline__ void tiles_body(const VoxParams& P, const int tile_id
                     __syncwarp();
                 }
             }
-            store_lane<CH, O16>(P, out_mol, plane, D, x, y, z, c0, acc, valid);
+            store_lane<CH, O16, CL>(P, out_mol, plane, D, x, y, z, c0, acc, valid);
         }
     }
 }
 
-template <int MODE, int CH, bool BINARY, bool O16>
+template <int MODE, int CH, bool BINARY, bool O16, bool CL>
 __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_tiles_kernel(const VoxParams P) {
-    tiles_body<MODE, CH, BINARY, O16>(P, (int)blockIdx.x);
+    tiles_body<MODE, CH, BINARY, O16, CL>(P, (int)blockIdx.x);
 }
 
 // Companion of the pipelined form: a small grid scans the tile descriptors and does, with the tile form's
 // multi-round staging, the few tiles that have more entries than the pipelined form takes (usually none).
 constexpr int kSweepList = 64;
-template <int MODE, int CH, bool BINARY, bool O16>
+template <int MODE, int CH, bool BINARY, bool O16, bool CL>
 __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_sweep_kernel(const VoxParams P, const unsigned ntiles) {
     __shared__ int s_list[kSweepList];
     __shared__ int s_n;
@@ -984,13 +984,13 @@ __global__ void __launch_bounds__(kThreads, 2) mvx_voxelize_sweep_kernel(const V
     if (n == 0) return;
     if (n <= kSweepList) {
         for (int i = 0; i < n; ++i) {
-            tiles_body<MODE, CH, BINARY, O16>(P, s_list[i]);
+            tiles_body<MODE, CH, BINARY, O16, CL>(P, s_list[i]);
             __syncthreads();
         }
     } else {   // more overflow tiles than the list holds: walk the chunk
         for (unsigned t = t0; t < t1; ++t) {
             if (P.tdesc[t].total > (uint32_t)P.pipe_sc) {
-                tiles_body<MODE, CH, BINARY, O16>(P, (int)t);
+                tiles_body<MODE, CH, BINARY, O16, CL>(P, (int)t);
                 __syncthreads();
             }
         }
@@ -1093,7 +1093,7 @@ __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory");
 }
 
-template <int MODE, int CH, bool BINARY, bool O16, bool MULTI>
+template <int MODE, int CH, bool BINARY, bool O16, bool MULTI, bool CL>
 __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(const VoxParams P, const unsigned ntiles) {
     constexpr int LPR = 4, RX = kCellX, RY = kCellY, CZ = kCellZ;
     constexpr int NCY = kTile / RY;
@@ -1388,7 +1388,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
                         for (int k = 0; k < 4; ++k) acc[c][k] = 0.f;
                 };
                 auto store = [&](const int c0) {
-                    store_lane<CH, O16>(P, out_mol, plane, D, x, y, z, c0, acc, valid);
+                    store_lane<CH, O16, CL>(P, out_mol, plane, D, x, y, z, c0, acc, valid);
                 };
 
                 // When the whole layer fits one warp list (the common case) its hit masks serve every channel chunk;
@@ -1408,7 +1408,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mvx_voxelize_pipe_kernel(cons
                 if (tid == 0) produce(false);   // keep the ring topped up without ever blocking
             }
         } else if (total == 0u) {
-            zero_tile<O16, kPipeThreads>(P, reinterpret_cast<char*>(P.out) + (size_t)mol * P.Cout * plane * es, plane, D, x0, y0, z0, z1, tid);
+            zero_tile<O16, kPipeThreads, CL>(P, reinterpret_cast<char*>(P.out) + (size_t)mol * P.Cout * plane * es, plane, D, x0, y0, z0, z1, tid);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);

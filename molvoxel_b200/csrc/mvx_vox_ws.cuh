@@ -254,7 +254,7 @@ __global__ void __launch_bounds__((NB + NWK) * 32, 1) mvx_voxelize_ws_kernel(con
                     if (tid == 0) produce(false);
                 }
             } else if (total == 0u) {
-                zero_tile<O16, NB * 32>(P, reinterpret_cast<char*>(P.out) + (size_t)sDesc[s].mol * P.Cout * plane * es, plane, D, x0, y0, z0, z1, tid);
+                zero_tile<O16, NB * 32, false>(P, reinterpret_cast<char*>(P.out) + (size_t)sDesc[s].mol * P.Cout * plane * es, plane, D, x0, y0, z0, z1, tid);
             }
             // end of tile for this builder; a tile without cells has no accumulator-side arrival: thread 0 stands in
             __syncwarp();
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__((NB + NWK) * 32, 1) mvx_voxelize_ws_kernel(con
                 }
                 walk(hm0, hm1, hm2, hm3, c0);
             }
-            store_lane<CH, O16>(P, out_mol, plane, D, x, y, z, c0, acc, valid);
+            store_lane<CH, O16, false>(P, out_mol, plane, D, x, y, z, c0, acc, valid);
         }
         __syncwarp();
         if (lane == 0) {
