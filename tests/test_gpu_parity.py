@@ -1073,12 +1073,13 @@ def test_compact_collation_gives_identical_grids():
     assert nbytes(small) < 0.4 * nbytes(plain)
 
 
-def test_two_stream_form_equals_the_single_stream_form_bitwise():
+@pytest.mark.parametrize("C", [9, 16], ids=["c9", "c16"])
+def test_two_stream_form_equals_the_single_stream_form_bitwise(C):
     """mvx_voxelize_split (prep / binning of call k+1 on a second stream next to the voxelize kernel of call k, two
     workspaces, register-capped ligand kernel) over a sequence of distinct batches: identical grids, device inputs with
     inputs_ready=True and pinned host inputs with non_blocking=True; status flags still arrive."""
-    rng = np.random.default_rng(44)
-    C, B = 9, 96
+    rng = np.random.default_rng(44 + C)
+    B = 96
     batches = [ligand_batch(rng, B, C) for _ in range(5)]
     plain = mv.create_voxelizer(0.5, 64, "scalar", "gaussian", library="b200", overlap=False)
     fast = mv.create_voxelizer(0.5, 64, "scalar", "gaussian", library="b200")
@@ -1100,7 +1101,7 @@ def test_two_stream_form_equals_the_single_stream_form_bitwise():
     for k, ((o, c, t), g) in enumerate(zip(batches, got)):
         assert torch.equal(g, plain.forward_types_batch(c, o, None, t, 1.0, C, random_translation=0.5, random_rotation=True, rng_offset=7 * k))
     bad = batches[0][2].copy()
-    bad[5] = 11
+    bad[5] = C + 2
     fast.forward_types_batch(dev[0][0], dev[0][1], None, torch.from_numpy(bad).cuda(), 1.0, C, inputs_ready=True)
     with pytest.raises(ValueError):
         fast.check_status()
