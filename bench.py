@@ -45,7 +45,7 @@ WORKLOADS = {
     "cfg2b": dict(mode="features", C=16, dim=48, res=0.5, density="gaussian", radii_type="scalar", atoms=(2000, 2000), batch=256,
                   pool=8,
                   desc="cfg2 with the atoms in a Gaussian blob (sigma 4 A) instead of uniform: heterogeneous tiles (not a BASELINE config)"),
-    "cfg5": dict(mode="features", C=32, dim=96, res=0.375, density="gaussian", radii_type="atom-wise", atoms=(10000, 10000), batch=16,
+    "cfg5": dict(mode="features", C=32, dim=96, res=0.375, density="gaussian", radii_type="atom-wise", atoms=(10000, 10000), batch=32,
                  pool=4,
                  desc="large complex 10,000 atoms, forward_features C=32 dense, 96^3, res 0.375, atom-wise radii U[1,2]"),
 }
@@ -293,11 +293,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(name):
+def ncu_traffic(name, batch):
+    """DRAM bytes of one voxelize launch from the committed ncu capture; the capture's batch is recorded beside it and
+    the figure is only reported for that batch."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(name)
+            d = json.load(open(p))
+            return d.get(name) if int(d.get("batch", {}).get(name, -1)) == int(batch) else None
         except Exception:
             return None
     return None
@@ -602,7 +605,7 @@ def run_b200_arm(args):
                 "note": "public API with pinned HOST inputs (pool workloads: collated by molvoxel_b200.Collator(pinned=True, compact=True), which narrows losslessly where it can), every call: Voxelizer.forward_*_batch(non_blocking=True) = async H2D (copy stream, 2-deep staging ring) -> prep/bin/voxelize -> D2H of the status word; one sync at the end of the timed region. blocking_value = mvx_voxelize_host (one sync per call). Grids stay in HBM (reference torch-backend convention); with_grid_d2h* = grids delivered to host memory"},
         "gpu_launches": per_call * n_calls,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(name), "kernel": kernel_name, "kernel_ms": prof["vox"],
+                     "traffic": ncu_traffic(name, B), "kernel": kernel_name, "kernel_ms": prof["vox"],
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "write_only_reference_gbs": fill_gbs,
                      "note": "peak is the measured COPY bandwidth (read+write); this kernel only writes, so frac can exceed 1.0 — write_only_reference_gbs is torch zero_() (device memset) on the same buffers",

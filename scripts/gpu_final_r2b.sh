@@ -14,5 +14,5 @@ for wl in cfg3 cfg2 cfg5; do
 done
 bash scripts/gpu_profile.sh cfg4 1024 r2b > /dev/null 2>&1
 bash scripts/gpu_profile.sh cfg2 256 r2b > /dev/null 2>&1
-bash scripts/gpu_profile.sh cfg5 16 r2b > /dev/null 2>&1
+bash scripts/gpu_profile.sh cfg5 32 r2b > /dev/null 2>&1
 ls gpurun_out | head -50
