@@ -250,7 +250,8 @@ int make_plan(const mvx_grid_spec* s, const mvx_batch* b, Plan* pl) {
     pl->off_alayers = off;  off += align_up(layered(pl->form) ? N * sizeof(uint32_t) : 0);
     pl->off_lists = off;    off += align_up(layered(pl->form) ? 0 : N * (size_t)pl->maxcols * sizeof(uint32_t));
     pl->off_entries = off;  off += align_up(pl->form == FORM_CELLS ? N * (size_t)pl->maxcols * sizeof(mvx::ColEntry) : 0);
-    pl->off_wide = off;     off += align_up((b->mode == MVX_MODE_FEATURES && b->features_dtype != MVX_F32) ? N * (size_t)b->num_channels * sizeof(float) : 0);
+    // compact feature rows: the layered forms widen them inside the entry build; the others read a widened fp32 copy
+    pl->off_wide = off;     off += align_up((b->mode == MVX_MODE_FEATURES && b->features_dtype != MVX_F32 && !layered(pl->form)) ? N * (size_t)b->num_channels * sizeof(float) : 0);
     pl->total = off;
     return MVX_OK;
 }
@@ -330,7 +331,7 @@ int mvx_launches_per_call(const mvx_grid_spec* spec, const mvx_batch* batch) {
     int nvox = (chan_feat && batch->out_dtype != MVX_OUT_F64) ? batch->num_channels : 1;
     const int nbin = layered(pl.form) ? (batch->total_atoms > 0 ? 3 : 1) : (bin_groups(batch->num_mols, pl.ncol, batch->total_atoms) <= 1 ? 1 : 2);   // scan, place, build
     const int nexp = (pl.form == FORM_CELLS && batch->total_atoms > 0 && bin_groups(batch->num_mols, pl.ncol, batch->total_atoms) > 1) ? 1 : 0;   // fused into bin for big batches
-    const int nwide = (batch->mode == MVX_MODE_FEATURES && batch->features_dtype != MVX_F32 && batch->total_atoms > 0) ? 1 : 0;
+    const int nwide = (batch->mode == MVX_MODE_FEATURES && batch->features_dtype != MVX_F32 && batch->total_atoms > 0 && !layered(pl.form)) ? 1 : 0;
     return (batch->total_atoms > 0 ? 1 : 0) + nwide + nbin + nexp + nvox * (pl.form == FORM_PIPE ? 2 : 1);   // prep + bin + expand + voxelize
 }
 
@@ -372,7 +373,8 @@ int enqueue(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, void* 
     const int64_t N = batch->total_atoms;
     const int C = batch->mode == MVX_MODE_SINGLE ? 1 : batch->num_channels;
     mvx_batch wide;   // compact feature rows: widened to fp32 once, everything downstream reads the fp32 copy
-    if (batch->mode == MVX_MODE_FEATURES && batch->features_dtype != MVX_F32 && N > 0) {
+    const int feat_dtype = batch->features_dtype;   // as the caller passed them (the layered entry build widens compact rows itself)
+    if (batch->mode == MVX_MODE_FEATURES && batch->features_dtype != MVX_F32 && N > 0 && !layered(pl.form)) {
         float* dst = (float*)(ws + pl.off_wide);
         const size_t n = (size_t)N * (size_t)C;
         mvx::mvx_widen_features_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(batch->features, batch->features_dtype == MVX_F16, n, dst);
@@ -413,7 +415,11 @@ int enqueue(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, void* 
         lp.B = B; lp.ncol = pl.ncol; lp.ncx = pl.geo.ncx; lp.maxcols = pl.maxcols; lp.zl = pl.zl; lp.nl = pl.nlayers;
         lp.nzc = pl.nzc; lp.tz = pl.tz; lp.dim = spec->dimension; lp.mode = batch->mode;
         lp.C = batch->mode == MVX_MODE_FEATURES ? C : 0; lp.es4 = pl.es4;
-        lp.feat_vec = (C % 4 == 0) && ((uintptr_t)batch->features % 16 == 0);
+        lp.feat_dtype = batch->mode == MVX_MODE_FEATURES ? feat_dtype : MVX_F32;
+        {   // four elements per load: 16 / 4 / 8-byte aligned rows for f32 / u8 / f16
+            const uintptr_t al = lp.feat_dtype == MVX_U8 ? 4 : (lp.feat_dtype == MVX_F16 ? 8 : 16);
+            lp.feat_vec = (C % 4 == 0) && ((uintptr_t)batch->features % al == 0);
+        }
         lp.mol_offsets = batch->mol_offsets; lp.colrange = colrange; lp.alayers = (const uint32_t*)(ws + pl.off_alayers);
         lp.recs = recs; lp.types = batch->types; lp.features = (const float*)batch->features;
         lp.bins = bins; lp.lbins = (uint2*)(ws + pl.off_lbins);

@@ -388,7 +388,8 @@ struct LBinParams {
     double res, half_width, sigma;
     float tau_lin, tau_quad;
     int B, ncol, ncx, maxcols, zl, nl, nzc, tz, dim, mode, C, es4;
-    int feat_vec;   // feature rows can be read as float4 (C % 4 == 0 and a 16-byte aligned base)
+    int feat_vec;   // feature rows can be read four elements at a time (C % 4 == 0 and a base aligned to four elements)
+    int feat_dtype; // element type of `features`: MVX_F32 0 | MVX_U8 2 | MVX_F16 3 — compact rows are widened here, exactly
     int64_t N;
     const int32_t* mol_offsets;
     const uint32_t* colrange;
@@ -553,11 +554,36 @@ __global__ void __launch_bounds__(256) mvx_lbuild_kernel(const LBinParams P) {
         e2 = make_float4(__uint_as_float(n), __uint_as_float(cm), 0.f, 0.f);
         return cm;
     };
-    auto feature_word = [&](const float* f, const int k) -> float4 {   // word k of the padded feature row
-        if (P.feat_vec) return 4 * k < P.C ? __ldg(reinterpret_cast<const float4*>(f) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float v[4];
+    // word k (4 channels) of atom n's padded feature row, as fp32.  Compact rows (u8 / f16) are widened here, exactly — the
+    // reference's features.astype(float32), numpy/voxelizer.py:127-128 — so dense batches need no separate widening pass.
+    auto feature_word = [&](const size_t n, const int k) -> float4 {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (4 * k >= P.C) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const size_t at = n * (size_t)P.C + (size_t)(4 * k);
+        if (P.feat_dtype == 0) {
+            const float* f = P.features + at;
+            if (P.feat_vec) return __ldg(reinterpret_cast<const float4*>(f));
 #pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] = (4 * k + c < P.C) ? __ldg(f + 4 * k + c) : 0.f;
+            for (int c = 0; c < 4; ++c) v[c] = (4 * k + c < P.C) ? __ldg(f + c) : 0.f;
+        } else if (P.feat_dtype == 2) {
+            const unsigned char* f = reinterpret_cast<const unsigned char*>(P.features) + at;
+            if (P.feat_vec) {
+                const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(f));
+                return make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[c] = (4 * k + c < P.C) ? (float)__ldg(f + c) : 0.f;
+        } else {
+            const __half* f = reinterpret_cast<const __half*>(P.features) + at;
+            if (P.feat_vec) {
+                const uint2 u = __ldg(reinterpret_cast<const uint2*>(f));
+                const __half2 a = *reinterpret_cast<const __half2*>(&u.x), b = *reinterpret_cast<const __half2*>(&u.y);
+                const float2 fa = __half22float2(a), fb = __half22float2(b);
+                return make_float4(fa.x, fa.y, fb.x, fb.y);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[c] = (4 * k + c < P.C) ? __half2float(f[c]) : 0.f;
+        }
         return make_float4(v[0], v[1], v[2], v[3]);
     };
 
@@ -586,11 +612,10 @@ __global__ void __launch_bounds__(256) mvx_lbuild_kernel(const LBinParams P) {
                 float4* e = stage + lane * ES4;
                 // the first four feature words are requested before the record arithmetic (independent loads in
                 // flight together); wider rows follow in groups of four
-                const float* f = P.features + (size_t)n * P.C;
                 const int nf = P.mode == 2 ? ES4 - 3 : 0;
                 float4 fw[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) fw[k] = k < nf ? feature_word(f, k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < 4; ++k) fw[k] = k < nf ? feature_word(n, k) : make_float4(0.f, 0.f, 0.f, 0.f);
                 float4 e0, e1, e2;
                 make_entry(n, e0, e1, e2);
                 e[0] = e0; e[1] = e1; e[2] = e2;
@@ -599,7 +624,7 @@ __global__ void __launch_bounds__(256) mvx_lbuild_kernel(const LBinParams P) {
                     if (k < nf) e[3 + k] = fw[k];
                 for (int k0 = 4; k0 < nf; k0 += 4) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) fw[k] = k0 + k < nf ? feature_word(f, k0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int k = 0; k < 4; ++k) fw[k] = k0 + k < nf ? feature_word(n, k0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         if (k0 + k < nf) e[3 + k0 + k] = fw[k];
@@ -639,8 +664,7 @@ __global__ void __launch_bounds__(256) mvx_lbuild_kernel(const LBinParams P) {
         float4* e = P.lent + slot * (size_t)ES4;
         e[0] = e0; e[1] = e1; e[2] = e2;
         if (P.mode == 2) {
-            const float* f = P.features + (size_t)n * P.C;
-            for (int k = 0; k < ES4 - 3; ++k) e[3 + k] = feature_word(f, k);
+            for (int k = 0; k < ES4 - 3; ++k) e[3 + k] = feature_word(n, k);
         }
     }
 }
