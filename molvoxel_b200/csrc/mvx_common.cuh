@@ -1,4 +1,5 @@
-// mvx_kernels.cuh — sm_100a kernels of the voxelization hot path.
+// mvx_common.cuh — shared types and geometry of the sm_100a kernels of the voxelization hot path
+// (kernels: mvx_bin_kernels.cuh, mvx_vox_kernels.cuh, mvx_rigid.cuh; experiment: mvx_vox_ws.cuh).
 //
 // Path restated (semantics only; the structure is new): reference molvoxel/voxelizer/numpy/voxelizer.py
 //   prologue + clip + block cull  :263-295, :481-527   -> mvx_prep_kernel   (one thread per atom, fp64)
@@ -13,7 +14,8 @@
 //                                                         mvx_voxelize_kernel        generic (any D);  mvx_voxelize_f64_kernel  precision=64
 //
 // Data layout in HBM
-//   out      (B, Cout, D, H, W) fp32 (bf16 / fp16 / fp64 by out_dtype), W contiguous (reference layout, numpy/voxelizer.py:60-70)
+//   out      (B, Cout, D, H, W) fp32 (bf16 / fp16 / fp64 by out_dtype), W contiguous (reference layout, numpy/voxelizer.py:60-70);
+//            (B, D, H, W, Cout) with out_layout = DHWC (channels-last instances of the same kernels)
 //   AtomRec  40 B per atom: centred fp64 position, fp32 radius, cull "forbidden planes", z voxel range
 //   lists    uint32 atom ids per (molecule, 8x8 voxel column), ascending = the reference's atom order (ligand batches)
 //   lent     layered entries per (molecule, column, 16-voxel z layer), record + feature row, ascending atom order (dense batches)
