@@ -457,7 +457,10 @@ int enqueue(const mvx_grid_spec* spec, const mvx_batch* batch, void* out, void* 
         ep.types = batch->types; ep.entries = entries;
         const bool expand = pl.form == FORM_CELLS && N > 0;
         if (groups <= 1 && expand) {   // many small molecules: bin and expand in one launch
-            mvx::mvx_bin_expand_kernel<<<(unsigned)B, pt, smem, st>>>(bp, ep);
+            // a handful of molecules (the reference's one-molecule-per-call pattern): one CTA each cannot fill the GPU, so
+            // give it 32 warps — 2 of a 64^3 grid's 64 columns per warp instead of 8 (the call is latency, not throughput)
+            const int ptb = (!split && B <= 74) ? 1024 : pt;
+            mvx::mvx_bin_expand_kernel<<<(unsigned)B, ptb, smem, st>>>(bp, ep);
         } else if (groups <= 1) {
             mvx::mvx_bin_kernel<<<(unsigned)B, pt, smem, st>>>(bp);
         } else {   // few large molecules: spread each molecule's columns over several CTAs

@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256) mvx_expand_kernel(const ExpandParams P) {
 
 // Fused form for many small molecules (ligand batches): one CTA per molecule counts, scans, fills its column lists and
 // expands each of them right away (the warp that filled a list turns it into entries), one launch instead of two.
-__global__ void mvx_bin_expand_kernel(const BinParams P, const ExpandParams E) {
+__global__ void __launch_bounds__(1024) mvx_bin_expand_kernel(const BinParams P, const ExpandParams E) {
     extern __shared__ uint32_t s_u32[];
     uint32_t* s_cnt = s_u32;            // [ncol]
     uint32_t* s_off = s_u32 + P.ncol;   // [ncol]

@@ -327,8 +327,14 @@ class Voxelizer:
 
     # ---- implementation ----
     def _spec(self):
-        return _lib.GridSpec(float(self._resolution), int(self._dimension), _lib.DENSITY[self._density_type],
-                             float(self._sigma), _lib.RADII[self._radii_type], int(self.blockdim))
+        """mvx_grid_spec of the current settings (rebuilt only when one of them changed: the setters are plain attributes)."""
+        key = (self._resolution, self._dimension, self._density_type, self._sigma, self._radii_type, self.blockdim)
+        cached = getattr(self, "_spec_cache", None)
+        if cached is None or cached[0] != key:
+            cached = (key, _lib.GridSpec(float(self._resolution), int(self._dimension), _lib.DENSITY[self._density_type],
+                                         float(self._sigma), _lib.RADII[self._radii_type], int(self.blockdim)))
+            self._spec_cache = cached
+        return cached[1]
 
     def _workspace(self, nbytes: int) -> torch.Tensor:
         if self._ws is None or self._ws.numel() < nbytes:
@@ -607,7 +613,9 @@ class Voxelizer:
         split = (on_device and inputs_ready is not None and inputs_ready is not False and not converted[0] and tf_rows is None
                  and mode == "types" and 9 <= out_channels <= 16 and self.out_dtype != torch.float64
                  and L.mvx_voxelize_form(ctypes.byref(spec), ctypes.byref(b)) == 1)
-        cur = torch.cuda.current_stream(self.device)
+        cur = torch.cuda.current_stream(self.device) if split else None
+        # the caller's current stream as a raw handle (what the C ABI takes); the Stream object is only needed by the two-stream form
+        raw_stream = cur.cuda_stream if split else torch._C._cuda_getCurrentRawStream(self.device.index)
         if split:
             ov = self._overlap
             if ov is None:
@@ -641,7 +649,7 @@ class Voxelizer:
                         t.record_stream(bs)
                 return rc
             fn = L.mvx_voxelize if on_device else L.mvx_voxelize_host
-            return fn(*args, ctypes.c_void_p(cur.cuda_stream))
+            return fn(*args, ctypes.c_void_p(raw_stream))
         if torch.cuda.current_device() == self.device.index:
             rc = launch()
         else:
@@ -650,13 +658,11 @@ class Voxelizer:
         _lib.raise_for_status(rc)
         # shapes / flags of this call (pointers are not dereferenced again): compact() finds the column occupancy the
         # binning pass left in the workspace
-        last = _lib.Batch()
-        ctypes.memmove(ctypes.byref(last), ctypes.byref(b), ctypes.sizeof(b))
-        self._last_call = (spec, last, ws_ptr, out.data_ptr())
+        self._last_call = (spec, b, ws_ptr, out.data_ptr())   # b is this call's own struct: never written again
         if on_device:
             for t in keep:   # inputs converted on the fly must outlive the asynchronous kernels
-                if isinstance(t, torch.Tensor):
-                    t.record_stream(torch.cuda.current_stream(self.device))
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(cur if cur is not None else torch.cuda.current_stream(self.device))
         return out
 
     # ---- brick-sparse grids for host-side consumers (molvoxel_b200/sparse.py) ----
