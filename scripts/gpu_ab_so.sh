@@ -10,7 +10,7 @@ import json, sys
 try:
     d = json.load(open("/tmp/ab.json"))
     r = d["roofline"]
-    print(f"{sys.argv[1]} {sys.argv[2]}: kernel_ms {r['kernel_ms']:.4f} frac {r['frac']:.3f} bin_ms {r['step_share']['bin_ms']:.4f} prep_ms {r['step_share']['prep_ms']:.4f} value {d['value']:.0f} e2e {d['e2e']['value']:.0f} parity {d['parity'].get('ok')} err {d['parity'].get('max_abs_err_over_peak')}")
+    print(f"{sys.argv[1]} {sys.argv[2]}: kernel_ms {r['kernel_ms']:.4f} frac {r['frac']:.3f} bin_ms {r['step_share']['bin_ms']:.4f} prep_ms {r['step_share']['prep_ms']:.4f} value {d['value']:.0f} e2e {d['e2e']['value']:.0f} parity {(d.get('parity') or {}).get('ok')} err {(d.get('parity') or {}).get('max_abs_err_over_peak')}")
 except Exception as e:
     print(sys.argv[1], sys.argv[2], "FAILED", e)
 PY
